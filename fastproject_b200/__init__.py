@@ -1,0 +1,23 @@
+# -*- coding: utf-8 -*-
+"""fastproject_b200 -- B200-native scoring core of FastProject.
+
+Drop-in for the reference's data-parallel hot path only:
+
+    from fastproject_b200 import SigScoreMethods, Signatures
+
+mirrors ``FastProject.SigScoreMethods`` / ``FastProject.Signatures`` (scoring
+half).  All arithmetic runs in hand-written sm_100a CUDA kernels behind the C
+ABI of ``include/fastproject_b200.h``; there is no CPU fallback.
+"""
+from . import Global  # noqa: F401  (seeds the global ``random`` stream like the reference)
+
+__version__ = "0.1.0"
+__all__ = ["SigScoreMethods", "Signatures", "Global", "synth"]
+
+
+def __getattr__(name):
+    # SigScoreMethods / Signatures import torch; keep ``import fastproject_b200`` light
+    if name in ("SigScoreMethods", "Signatures", "synth", "distributed"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(name)

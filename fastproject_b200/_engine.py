@@ -1,0 +1,187 @@
+# -*- coding: utf-8 -*-
+"""Device plumbing between the Python mirror of the reference API and the
+C ABI: PyTorch tensors carry the buffers (allocation, H2D/D2H copies, the
+current stream); every computation is a call into libfastproject_b200.so.
+
+There is no CPU path here: a missing GPU or library raises.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _native
+
+_ROW_ALIGN = 32          # leading dimension of every [signatures x cells] matrix, in elements
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _native.NativeError("fastproject_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def padded(n):
+    return (int(n) + _ROW_ALIGN - 1) // _ROW_ALIGN * _ROW_ALIGN
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def default_precision():
+    return os.environ.get("FASTPROJECT_B200_PRECISION", "fp64")
+
+
+# --------------------------------------------------------------------------
+# host -> device
+# --------------------------------------------------------------------------
+def to_device(arr, dtype=torch.float64):
+    """NumPy array or CPU/GPU torch tensor -> contiguous CUDA tensor."""
+    dev = require_cuda()
+    if isinstance(arr, torch.Tensor):
+        t = arr
+    else:
+        a = np.asarray(arr)
+        if a.dtype == np.bool_:
+            a = a.astype(np.float64)
+        if not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a)
+    t = t.to(device=dev, dtype=dtype, non_blocking=True)
+    return t.contiguous()
+
+
+class _ExpressionCache(object):
+    """Keeps the last few genes x cells matrices resident in HBM so that the
+    two calculate_sig_scores calls of the pipeline (real, then random
+    signatures; Pipelines.py:204,229) upload X and W once.  An entry is reused
+    only if the host array has the same address, shape, strides and a matching
+    fingerprint (corner + strided samples); set FASTPROJECT_B200_NO_CACHE=1 to
+    disable."""
+
+    def __init__(self, capacity=6):
+        self.capacity = capacity
+        self.entries = []          # list of (key, fingerprint, tensor)
+
+    @staticmethod
+    def _key(a):
+        if isinstance(a, torch.Tensor):
+            return ("t", a.data_ptr(), tuple(a.shape), tuple(a.stride()), str(a.dtype), str(a.device))
+        a = np.asarray(a)
+        return ("n", a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+
+    @staticmethod
+    def _fingerprint(a):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return None
+            a = a.numpy()
+        a = np.asarray(a)
+        flat_n = a.size
+        if flat_n == 0:
+            return b""
+        step = max(1, flat_n // 4099)
+        idx = np.arange(0, flat_n, step, dtype=np.int64)
+        sample = a.reshape(-1)[idx] if a.flags["C_CONTIGUOUS"] else a.T.reshape(-1)[idx]
+        return np.ascontiguousarray(sample).tobytes()
+
+    def get(self, a):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.to(torch.float64).contiguous()
+        if os.environ.get("FASTPROJECT_B200_NO_CACHE"):
+            return to_device(a)
+        key, fp = self._key(a), self._fingerprint(a)
+        for i, (k, f, t) in enumerate(self.entries):
+            if k == key and f == fp:
+                self.entries.append(self.entries.pop(i))
+                return t
+        t = to_device(a)
+        self.entries.append((key, fp, t))
+        while len(self.entries) > self.capacity:
+            self.entries.pop(0)
+        return t
+
+    def clear(self):
+        self.entries = []
+
+
+expression_cache = _ExpressionCache()
+
+
+def clear_device_cache():
+    expression_cache.clear()
+
+
+# --------------------------------------------------------------------------
+# kernels
+# --------------------------------------------------------------------------
+def score_signatures(method, x, w, z, sig_ptr, sig_gene, sig_sign, n_sigs):
+    """x, w, z: G x N CUDA float64 (w / z may be None); CSR arrays on device.
+    Returns a [n_sigs x ld] CUDA tensor (ld = padded N)."""
+    g, n = x.shape
+    ld = padded(n)
+    out = torch.zeros((n_sigs, ld), dtype=torch.float64, device=x.device)
+    if n_sigs == 0:
+        return out
+    mu = None
+    if method == "imputed":
+        mu = torch.empty((g,), dtype=torch.float64, device=x.device)
+        _native.call("fp_gene_detected_mean", ptr(x), ptr(z), g, n, x.stride(0), ptr(mu), stream_ptr())
+    _native.call("fp_score_signatures", _native.METHOD_CODES[method], ptr(x), ptr(w), ptr(z),
+                 g, n, x.stride(0), ptr(sig_ptr), ptr(sig_gene), ptr(sig_sign), n_sigs,
+                 ptr(mu), ptr(out), ld, stream_ptr())
+    return out
+
+
+def rank_rows(scores, n):
+    """scores: [K x ld] CUDA float64 -> average ranks, same shape."""
+    k, ld = scores.shape
+    out = torch.zeros_like(scores)
+    if k == 0:
+        return out
+    nbytes = _native.query("fp_rank_workspace_bytes", k, n, ld)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=scores.device)
+    _native.call("fp_rank_columns", ptr(scores), k, n, ld, ptr(out), ptr(ws), nbytes, stream_ptr())
+    return out
+
+
+def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_ABS_ERROR,
+                precision=None):
+    """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor."""
+    k, ld = ranks.shape
+    if out is None:
+        out = torch.empty((k, ld), dtype=torch.float64, device=ranks.device)
+    mode = _native.PRECISION_CODES[precision or default_precision()]
+    vec = sigma_sq if isinstance(sigma_sq, torch.Tensor) else None
+    scalar = 0.0 if vec is not None else float(sigma_sq)
+    nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=ranks.device) if nbytes else None
+    _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
+                 ptr(out), out.stride(0), output_kind, mode, ptr(ws), nbytes, stream_ptr())
+    return out
+
+
+def row_medians(values, n):
+    k, ld = values.shape
+    out = torch.empty((k,), dtype=torch.float64, device=values.device)
+    _native.call("fp_row_medians", ptr(values), k, n, ld, ptr(out), stream_ptr())
+    return out
+
+
+def background_pvalues(med, sig_group, rnd_med, rnd_order, group_ptr):
+    """All arguments CUDA tensors (float64 / int32).  Returns (p, mu, sigma)."""
+    k = med.shape[0]
+    n_groups = group_ptr.shape[0] - 1
+    p = torch.empty((k,), dtype=torch.float64, device=med.device)
+    mu = torch.empty((max(n_groups, 1),), dtype=torch.float64, device=med.device)
+    sd = torch.empty((max(n_groups, 1),), dtype=torch.float64, device=med.device)
+    _native.call("fp_background_pvalues", ptr(med), ptr(sig_group), k, ptr(rnd_med), ptr(rnd_order),
+                 ptr(group_ptr), n_groups, ptr(p), ptr(mu), ptr(sd), stream_ptr())
+    return p, mu, sd

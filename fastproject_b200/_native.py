@@ -1,0 +1,83 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of the C ABI declared in include/fastproject_b200.h.
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, an exception is raised.  Build it with ``python __graft_entry__.py``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libfastproject_b200.so")
+
+c_i64 = ctypes.c_int64
+c_f64 = ctypes.c_double
+c_ptr = ctypes.c_void_p
+c_int = ctypes.c_int
+c_size = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/fastproject_b200.h declares
+SIGNATURES = {
+    "fp_abi_version": (c_int, []),
+    "fp_version": (ctypes.c_char_p, []),
+    "fp_last_error": (ctypes.c_char_p, []),
+    "fp_launch_count": (ctypes.c_uint64, []),
+    "fp_gene_detected_mean": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "fp_score_signatures": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
+                                    c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    "fp_rank_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "fp_rank_columns": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
+    "fp_consistency_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
+    "fp_consistency": (c_int, [c_ptr, c_ptr, c_f64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64,
+                               c_int, c_int, c_ptr, c_size, c_ptr]),
+    "fp_row_medians": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "fp_background_pvalues": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
+                                      c_ptr, c_ptr, c_ptr, c_ptr]),
+}
+
+METHOD_CODES = {"naive": 0, "weighted_avg": 1, "imputed": 2, "only_nonzero": 3}
+PRECISION_CODES = {"fp64": 0, "tf32x3": 1}
+OUT_ABS_ERROR, OUT_PREDICTION = 0, 1
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (idempotent).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "fastproject_b200: %s not found -- the CUDA extension is not built "
+            "(run `python __graft_entry__.py`); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise NativeError on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.fp_last_error()
+        raise NativeError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else ""))
+
+
+def query(name, *args):
+    return getattr(load(), name)(*args)
+
+
+def launch_count():
+    return int(load().fp_launch_count())

@@ -1,0 +1,162 @@
+# -*- coding: utf-8 -*-
+"""Host-side logic of the scoring half of the path: signature -> CSR packing
+(replacing the O(G) Python loop of Signature.sig_indices,
+/root/reference/FastProject/Signatures.py:738-753), the device-resident
+``ScoreBatch`` and its lazy host views."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _engine
+
+METHODS = ("naive", "weighted_avg", "imputed", "only_nonzero")
+
+
+def gene_row_index(row_labels):
+    """gene label -> row (int) or rows (list) if the label is duplicated.  The
+    reference loop (:747-753) visits every row, so duplicates all match."""
+    index = dict()
+    for pos, gene in enumerate(row_labels):
+        prev = index.get(gene)
+        if prev is None:
+            index[gene] = pos
+        elif isinstance(prev, list):
+            prev.append(pos)
+        else:
+            index[gene] = [prev, pos]
+    return index
+
+
+def signature_rows(sig_dict, index):
+    """Matched (rows ascending, signs) of one signature.  A dict value equal to
+    1 or 0 counts as +1, equal to -1 as -1, anything else is ignored (:750-753)."""
+    rows, signs = [], []
+    for gene, val in sig_dict.items():
+        hit = index.get(gene)
+        if hit is None:
+            continue
+        if val == 1 or val == 0:
+            s = 1
+        elif val == -1:
+            s = -1
+        else:
+            continue
+        if isinstance(hit, list):
+            rows.extend(hit)
+            signs.extend([s] * len(hit))
+        else:
+            rows.append(hit)
+            signs.append(s)
+    if len(rows) > 1:
+        order = np.argsort(np.asarray(rows, dtype=np.int64), kind="stable")
+        rows = np.asarray(rows, dtype=np.int32)[order]
+        signs = np.asarray(signs, dtype=np.int8)[order]
+    else:
+        rows = np.asarray(rows, dtype=np.int32)
+        signs = np.asarray(signs, dtype=np.int8)
+    return rows, signs
+
+
+def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject=False):
+    """list[Signature] -> (kept positions, sig_ptr, sig_gene, sig_sign, num_genes).
+    Signatures with no matched gene, or fewer than ``min_signature_genes``, are
+    rejected -- the reference raises ValueError for them
+    (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676)."""
+    index = gene_row_index(row_labels)
+    kept, ptr, genes, signs, counts = [], [0], [], [], []
+    for pos, sig in enumerate(signatures):
+        rows, sg = signature_rows(sig.sig_dict, index)
+        if rows.size == 0:
+            if raise_on_reject:
+                raise ValueError("No genes match signature")
+            continue
+        if rows.size < min_signature_genes:
+            if raise_on_reject:
+                raise ValueError("Too few genes match signature")
+            continue
+        kept.append(pos)
+        genes.append(rows)
+        signs.append(sg)
+        counts.append(rows.size)
+        ptr.append(ptr[-1] + rows.size)
+    if ptr[-1] >= 2 ** 31:
+        raise ValueError("signature membership table exceeds int32 indexing")
+    sig_ptr = np.asarray(ptr, dtype=np.int32)
+    sig_gene = np.concatenate(genes) if genes else np.zeros((0,), dtype=np.int32)
+    sig_sign = np.concatenate(signs) if signs else np.zeros((0,), dtype=np.int8)
+    return kept, sig_ptr, sig_gene, sig_sign, np.asarray(counts, dtype=np.int64)
+
+
+class ScoreBatch(object):
+    """Scores of many signatures on the same cells, resident on the device as a
+    [signatures x ld] float64 matrix (one signature per row)."""
+
+    def __init__(self, scores_dev, n_cells, num_genes):
+        self.scores_dev = scores_dev
+        self.n_cells = int(n_cells)
+        self.num_genes = num_genes
+        self._ranks_dev = None
+        self._host_scores = None
+        self._host_ranks = None
+
+    def ranks_dev(self):
+        if self._ranks_dev is None:
+            self._ranks_dev = _engine.rank_rows(self.scores_dev, self.n_cells)
+        return self._ranks_dev
+
+    def host_scores(self):
+        if self._host_scores is None:
+            self._host_scores = self.scores_dev[:, :self.n_cells].cpu().numpy()
+        return self._host_scores
+
+    def host_ranks(self):
+        if self._host_ranks is None:
+            self._host_ranks = self.ranks_dev()[:, :self.n_cells].cpu().numpy()
+        return self._host_ranks
+
+
+def _matrix_of(data):
+    base = getattr(data, "base", None)
+    if base is None or (isinstance(data, np.ndarray) and not hasattr(data, "row_labels")):
+        base = data
+    return base
+
+
+def score_batch(data, signatures, method, zero_locations, min_signature_genes,
+                raise_on_reject=False):
+    """Score ``signatures`` on ``data``; returns a ScoreBatch whose ``kept``
+    lists the positions (into ``signatures``) that survived."""
+    if method not in METHODS:
+        raise KeyError(method)
+    kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
+        signatures, data.row_labels, min_signature_genes, raise_on_reject)
+    _engine.require_cuda()
+    x = _engine.expression_cache.get(_matrix_of(data))
+    n_genes, n_cells = x.shape
+    w = z = None
+    if method in ("weighted_avg", "imputed"):
+        w = _engine.expression_cache.get(data.weights)
+        if tuple(w.shape) != (n_genes, n_cells):
+            raise ValueError("weights shape %s != data shape %s" % (tuple(w.shape), (n_genes, n_cells)))
+    if method in ("imputed", "only_nonzero"):
+        if zero_locations is None:
+            raise TypeError("method %r needs zero_locations" % method)
+        z = _engine.expression_cache.get(zero_locations)
+    d_ptr = _engine.to_device(sig_ptr, torch.int32)
+    d_gene = _engine.to_device(sig_gene, torch.int32)
+    d_sign = _engine.to_device(sig_sign, torch.int8)
+    scores = _engine.score_signatures(method, x, w, z, d_ptr, d_gene, d_sign, len(kept))
+    batch = ScoreBatch(scores, n_cells, counts)
+    batch.kept = kept
+    return batch
+
+
+def rank_vector(values):
+    """Average ranks of one host vector through the device kernel."""
+    v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).ravel())
+    n = v.size
+    ld = _engine.padded(n)
+    dev = torch.zeros((1, ld), dtype=torch.float64, device=_engine.require_cuda())
+    dev[0, :n] = _engine.to_device(v)
+    return _engine.rank_rows(dev, n)[0, :n].cpu().numpy()

@@ -1,0 +1,75 @@
+// Library-level entry points: version, error text, launch counter, and the
+// precision-mode dispatch of fp_consistency.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "fp_common.cuh"
+
+int fp_consistency_fp64(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                        const double *ranks, int64_t N, int64_t K, int64_t ld, double *out_dissim,
+                        int64_t ld_out, int output_kind, cudaStream_t st);
+
+namespace fp {
+
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void clear_error() { g_error[0] = 0; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+}  // namespace fp
+
+extern "C" int fp_abi_version(void) { return FP_ABI_VERSION; }
+extern "C" const char *fp_version(void) { return "fastproject_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *fp_last_error(void) { return fp::g_error; }
+extern "C" uint64_t fp_launch_count(void) { return fp::g_launches.load(); }
+
+extern "C" size_t fp_consistency_workspace_bytes(int64_t N, int64_t K, int precision_mode) {
+    (void)N;
+    (void)K;
+    if (precision_mode == FP_PRECISION_FP64) return 0;
+    return 0;
+}
+
+extern "C" int fp_consistency(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                              const double *ranks, int64_t N, int64_t K, int64_t ld,
+                              double *out_dissim, int64_t ld_out, int output_kind,
+                              int precision_mode, void *workspace, size_t workspace_bytes, void *stream) {
+    fp::clear_error();
+    (void)workspace;
+    (void)workspace_bytes;
+    FP_CHECK_ARG(coords && ranks && out_dissim, "fp_consistency: null pointer");
+    FP_CHECK_ARG(N > 0 && K >= 0 && ld >= N && ld_out >= N,
+                 "fp_consistency: bad shape N=%ld K=%ld ld=%ld ld_out=%ld", (long)N, (long)K, (long)ld,
+                 (long)ld_out);
+    FP_CHECK_ARG(sigma_sq || sigma_sq_scalar > 0.0, "fp_consistency: sigma_sq must be positive");
+    FP_CHECK_ARG(output_kind == FP_OUT_ABS_ERROR || output_kind == FP_OUT_PREDICTION,
+                 "fp_consistency: unknown output kind %d", output_kind);
+    if (K == 0) return FP_OK;
+    if (precision_mode == FP_PRECISION_FP64)
+        return fp_consistency_fp64(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim,
+                                   ld_out, output_kind, fp::as_stream(stream));
+    fp::set_error("fp_consistency: precision mode %d not built", precision_mode);
+    return FP_EUNSUPPORTED;
+}

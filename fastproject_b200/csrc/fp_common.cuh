@@ -1,0 +1,88 @@
+// Shared helpers for the fastproject_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "fastproject_b200.h"
+
+namespace fp {
+
+// thread-local last-error text returned by fp_last_error()
+void set_error(const char *fmt, ...);
+void clear_error();
+void count_launch(int n = 1);
+
+// B200: 148 SMs.  Queried once; used to size persistent grids.
+int sm_count();
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define FP_CHECK_ARG(cond, ...)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            fp::set_error(__VA_ARGS__);          \
+            return FP_EINVAL;                    \
+        }                                        \
+    } while (0)
+
+#define FP_CHECK_CUDA(expr)                                                        \
+    do {                                                                           \
+        cudaError_t err__ = (expr);                                                \
+        if (err__ != cudaSuccess) {                                                \
+            fp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                          __FILE__, __LINE__);                                     \
+            return FP_ECUDA;                                                       \
+        }                                                                          \
+    } while (0)
+
+#define FP_CHECK_LAUNCH(name)                                                      \
+    do {                                                                           \
+        cudaError_t err__ = cudaGetLastError();                                    \
+        if (err__ != cudaSuccess) {                                                \
+            fp::set_error("launch of %s failed: %s", name, cudaGetErrorString(err__)); \
+            return FP_ECUDA;                                                       \
+        }                                                                          \
+        fp::count_launch();                                                        \
+    } while (0)
+
+// NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+// pairwise_sum_DOUBLE): < 8 elements sequential; <= 128 elements eight
+// interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then
+// a sequential tail; otherwise split at n/2 rounded down to a multiple of 8.
+// Reproduced so that row reductions (axis = contiguous axis) are bit-identical.
+template <typename Load>
+__device__ double np_pairwise_sum(Load load, long lo, long n) {
+    if (n < 8) {
+        double res = -0.0;                   // NumPy starts the short loop from -0.0
+        for (long i = 0; i < n; i++) res = __dadd_rn(res, load(lo + i));
+        return res;
+    } else if (n <= 128) {
+        double r0 = load(lo + 0), r1 = load(lo + 1), r2 = load(lo + 2), r3 = load(lo + 3);
+        double r4 = load(lo + 4), r5 = load(lo + 5), r6 = load(lo + 6), r7 = load(lo + 7);
+        long i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+            r0 = __dadd_rn(r0, load(lo + i + 0));
+            r1 = __dadd_rn(r1, load(lo + i + 1));
+            r2 = __dadd_rn(r2, load(lo + i + 2));
+            r3 = __dadd_rn(r3, load(lo + i + 3));
+            r4 = __dadd_rn(r4, load(lo + i + 4));
+            r5 = __dadd_rn(r5, load(lo + i + 5));
+            r6 = __dadd_rn(r6, load(lo + i + 6));
+            r7 = __dadd_rn(r7, load(lo + i + 7));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                               __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+        for (; i < n; i++) res = __dadd_rn(res, load(lo + i));
+        return res;
+    } else {
+        long n2 = n / 2;
+        n2 -= n2 % 8;
+        double a = np_pairwise_sum(load, lo, n2);
+        double b = np_pairwise_sum(load, lo + n2, n - n2);
+        return __dadd_rn(a, b);
+    }
+}
+
+}  // namespace fp

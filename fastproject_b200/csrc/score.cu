@@ -1,0 +1,164 @@
+// Signature scoring: K signatures x N cells in one launch.
+//
+// Replaces the bodies of naive/weighted/imputed/nonzero_eval_signature
+// (/root/reference/FastProject/SigScoreMethods.py:18-162) and the Python loop
+// of calculate_sig_scores (Signatures.py:669-679).
+//
+// Bit-exactness contract: the reference gathers the signature's rows in
+// ascending gene order and reduces with ndarray.sum(axis=0), which NumPy
+// evaluates row after row (sequential in g).  Every product below is a
+// separately rounded __dmul_rn and every accumulation a __dadd_rn in ascending
+// gene order, so no FMA contraction or reassociation can change a bit.
+#include "fp_common.cuh"
+
+namespace {
+
+// v1 mapping: one warp = one signature x 32 consecutive cells; lanes read
+// 256 contiguous bytes of a gene row (two full 128-byte lines) per operand.
+constexpr int kCellsPerBlock = 128;   // blockDim.x
+constexpr int kSigsPerBlock = 4;      // blockDim.y
+
+__device__ __forceinline__ double ldg_stream(const double *p) {
+    // read-only, keep out of L1 (each value is used once by this thread)
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kCellsPerBlock *kSigsPerBlock)
+score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
+                    const double *__restrict__ Z, long N, long ld,
+                    const int32_t *__restrict__ sig_ptr, const int32_t *__restrict__ sig_gene,
+                    const int8_t *__restrict__ sig_sign, long K,
+                    const double *__restrict__ gene_mu, double *__restrict__ out, long ld_out) {
+    const long cell = (long)blockIdx.x * kCellsPerBlock + threadIdx.x;
+    const bool live = cell < N;
+    const long c = live ? cell : (N - 1);
+    for (long k = (long)blockIdx.y * kSigsPerBlock + threadIdx.y; k < K;
+         k += (long)gridDim.y * kSigsPerBlock) {
+        const int beg = sig_ptr[k], end = sig_ptr[k + 1];
+        double num = 0.0, den = 0.0, aux = 0.0;
+        for (int t = beg; t < end; ++t) {
+            const long g = sig_gene[t];
+            const double s = (double)sig_sign[t];
+            const double x = ldg_stream(X + g * ld + c);
+            if (METHOD == FP_METHOD_NAIVE) {
+                // pdata = data * sig * ones ; norm = |sig| * ones   (:38-41)
+                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), 1.0));
+                den = __dadd_rn(den, 1.0);
+            } else if (METHOD == FP_METHOD_WEIGHTED) {
+                // pdata = data * sig * weights ; norm = |sig| * weights   (:70-73)
+                const double w = ldg_stream(W + g * ld + c);
+                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), w));
+                den = __dadd_rn(den, w);
+            } else if (METHOD == FP_METHOD_NONZERO) {
+                // (data * not_zeros) * sig ; norm = sum(not_zeros)   (:152-153)
+                const double nz = __dsub_rn(1.0, ldg_stream(Z + g * ld + c));
+                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
+                den = __dadd_rn(den, nz);
+            } else {  // FP_METHOD_IMPUTED (:105-121)
+                const double w = ldg_stream(W + g * ld + c);
+                const double z = ldg_stream(Z + g * ld + c);
+                const double nz = __dsub_rn(1.0, z);
+                const double mu = gene_mu[g];
+                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
+                const double t1 = __dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, w), mu), s), z);
+                const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(w, x), s), z);
+                aux = __dadd_rn(aux, __dadd_rn(t1, t2));
+            }
+        }
+        double score;
+        if (METHOD == FP_METHOD_NAIVE) {
+            score = __ddiv_rn(num, den);
+        } else if (METHOD == FP_METHOD_IMPUTED) {
+            score = __ddiv_rn(__dadd_rn(num, aux), (double)(end - beg));
+        } else {
+            if (den == 0.0) den = 1.0;           // norm_factor[norm_factor == 0] = 1.0
+            score = __ddiv_rn(num, den);
+        }
+        if (live) out[k * ld_out + cell] = score;
+    }
+}
+
+// mu_g over all cells, NumPy pairwise order (SigScoreMethods.py:109-111).
+// One block per gene: each thread reduces whole <=128-element leaves of the
+// pairwise tree, leaf sums are then combined in tree order by one thread.
+struct DetectedProduct {
+    const double *x, *z;
+    __device__ double operator()(long i) const { return __dmul_rn(x[i], __dsub_rn(1.0, z[i])); }
+};
+struct DetectedCount {
+    const double *z;
+    __device__ double operator()(long i) const { return __dsub_rn(1.0, z[i]); }
+};
+
+__global__ void gene_detected_mean_kernel(const double *__restrict__ X, const double *__restrict__ Z,
+                                          long G, long N, long ld, double *__restrict__ out_mu) {
+    // One warp-lane per gene keeps the recursion trivially exact; genes are
+    // spread over lanes so that the whole grid covers G.  This step is O(G*N)
+    // reads and runs once per data set (only for the "imputed" method).
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    DetectedProduct prod{X + g * ld, Z + g * ld};
+    DetectedCount cnt{Z + g * ld};
+    const double num = fp::np_pairwise_sum(prod, 0, N);
+    const double den = fp::np_pairwise_sum(cnt, 0, N);
+    double mu = __ddiv_rn(num, den);
+    if (mu != mu) mu = 0.0;                      // mu[np.isnan(mu)] = 0.0
+    out_mu[g] = mu;
+}
+
+}  // namespace
+
+extern "C" int fp_gene_detected_mean(const double *X, const double *Z, int64_t G, int64_t N,
+                                     int64_t ld, double *out_mu, void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(X && Z && out_mu, "fp_gene_detected_mean: null pointer");
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N, "fp_gene_detected_mean: bad shape G=%ld N=%ld ld=%ld",
+                 (long)G, (long)N, (long)ld);
+    const int threads = 32;
+    gene_detected_mean_kernel<<<(unsigned)((G + threads - 1) / threads), threads, 0,
+                                fp::as_stream(stream)>>>(X, Z, G, N, ld, out_mu);
+    FP_CHECK_LAUNCH("gene_detected_mean_kernel");
+    return FP_OK;
+}
+
+extern "C" int fp_score_signatures(int method, const double *X, const double *W, const double *Z,
+                                   int64_t G, int64_t N, int64_t ld, const int32_t *sig_ptr,
+                                   const int32_t *sig_gene, const int8_t *sig_sign, int64_t K,
+                                   const double *gene_mu, double *out_scores, int64_t ld_out,
+                                   void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(method >= FP_METHOD_NAIVE && method <= FP_METHOD_NONZERO,
+                 "fp_score_signatures: unknown method %d", method);
+    FP_CHECK_ARG(X && sig_ptr && sig_gene && sig_sign && out_scores,
+                 "fp_score_signatures: null pointer");
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N && K >= 0,
+                 "fp_score_signatures: bad shape G=%ld N=%ld ld=%ld K=%ld ld_out=%ld", (long)G,
+                 (long)N, (long)ld, (long)K, (long)ld_out);
+    FP_CHECK_ARG(method == FP_METHOD_NAIVE || method == FP_METHOD_NONZERO || W,
+                 "fp_score_signatures: method %d needs W", method);
+    FP_CHECK_ARG(method == FP_METHOD_NAIVE || method == FP_METHOD_WEIGHTED || Z,
+                 "fp_score_signatures: method %d needs Z", method);
+    FP_CHECK_ARG(method != FP_METHOD_IMPUTED || gene_mu, "fp_score_signatures: imputed needs gene_mu");
+    if (K == 0) return FP_OK;
+    dim3 block(kCellsPerBlock, kSigsPerBlock);
+    const long cell_tiles = (N + kCellsPerBlock - 1) / kCellsPerBlock;
+    long sig_tiles = (K + kSigsPerBlock - 1) / kSigsPerBlock;
+    if (sig_tiles > 65535) sig_tiles = 65535;
+    dim3 grid((unsigned)cell_tiles, (unsigned)sig_tiles);
+    cudaStream_t st = fp::as_stream(stream);
+#define FP_LAUNCH_SCORE(M)                                                                    \
+    score_gather_kernel<M><<<grid, block, 0, st>>>(X, W, Z, N, ld, sig_ptr, sig_gene, sig_sign, \
+                                                   K, gene_mu, out_scores, ld_out)
+    switch (method) {
+        case FP_METHOD_NAIVE: FP_LAUNCH_SCORE(FP_METHOD_NAIVE); break;
+        case FP_METHOD_WEIGHTED: FP_LAUNCH_SCORE(FP_METHOD_WEIGHTED); break;
+        case FP_METHOD_IMPUTED: FP_LAUNCH_SCORE(FP_METHOD_IMPUTED); break;
+        default: FP_LAUNCH_SCORE(FP_METHOD_NONZERO); break;
+    }
+#undef FP_LAUNCH_SCORE
+    FP_CHECK_LAUNCH("score_gather_kernel");
+    return FP_OK;
+}

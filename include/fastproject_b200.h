@@ -1,0 +1,177 @@
+/*
+ * fastproject_b200.h -- C ABI of the B200-native FastProject scoring core.
+ *
+ * The reference (YosefLab/FastProject v1.1.4) is pure Python and has no FFI /
+ * plugin layer of its own; the boundary it offers for this path is the Python
+ * call surface of FastProject/SigScoreMethods.py and FastProject/Signatures.py.
+ * Each entry point below names the reference code it replaces (paths relative
+ * to /root/reference/FastProject/).  The Python mirror of that call surface
+ * (fastproject_b200/SigScoreMethods.py, Signatures.py) binds these symbols with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in _host; no torch types, no C++ types, no exceptions;
+ *   - every function returns 0 on success or a negative FP_E* code and leaves
+ *     a message retrievable with fp_last_error() (thread-local);
+ *   - every launch goes to the caller's stream (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); no hidden device allocation:
+ *     scratch space is sized by the *_workspace_bytes() query and supplied by
+ *     the caller;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS.
+ *
+ * Device data layout
+ *   expression X, weights W, zero mask Z : genes x cells, float64, ld >= N
+ *       (the reference's ExpressionData.base / .weights / zero_locations,
+ *        DataTypes.py:16, Pipelines.py:148)
+ *   signatures : CSR over genes -- sig_ptr[K+1] (int32), sig_gene[nnz] (int32,
+ *       ascending inside a signature), sig_sign[nnz] (int8, +1/-1)
+ *       (replaces the dense G x 1 vector of Signature.sig_indices,
+ *        Signatures.py:738-753)
+ *   scores / ranks / dissimilarities : signatures x cells, float64 -- one
+ *       signature per ROW, cells contiguous (the transpose of the reference's
+ *       N x K sig_score_matrix, Signatures.py:359): the layout the segmented
+ *       sort, the TMA tiles of the consistency kernel and the per-signature
+ *       median all want
+ *   coordinates : 2 x N float64 (projections[name], Signatures.py:394)
+ */
+#ifndef FASTPROJECT_B200_H
+#define FASTPROJECT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP_ABI_VERSION 1
+
+/* error codes */
+#define FP_OK            0
+#define FP_EINVAL       -1   /* bad argument                                */
+#define FP_ECUDA        -2   /* CUDA runtime / launch error                 */
+#define FP_EWORKSPACE   -3   /* workspace too small                         */
+#define FP_EUNSUPPORTED -4   /* shape / mode not supported by this build    */
+
+/* scoring methods: Signatures.py:660-667 (method strings of calculate_sig_scores) */
+#define FP_METHOD_NAIVE        0   /* SigScoreMethods.py:18-48   "naive"        */
+#define FP_METHOD_WEIGHTED     1   /* SigScoreMethods.py:51-82   "weighted_avg" */
+#define FP_METHOD_IMPUTED      2   /* SigScoreMethods.py:85-128  "imputed"      */
+#define FP_METHOD_NONZERO      3   /* SigScoreMethods.py:131-162 "only_nonzero" */
+
+/* what fp_consistency writes */
+#define FP_OUT_ABS_ERROR       0   /* |r - prediction|  (Signatures.py:408, 413, 462, 470) */
+#define FP_OUT_PREDICTION      1   /* the prediction itself (factor branch, :493, 505)     */
+
+/* arithmetic of the neighbourhood contraction in fp_consistency */
+#define FP_PRECISION_FP64      0   /* float64 FMA on the FP64 pipe (verifier)           */
+#define FP_PRECISION_TF32X3    1   /* tcgen05 kind::tf32, hi/lo split, FP64 promotion   */
+
+int         fp_abi_version(void);
+const char *fp_version(void);
+const char *fp_last_error(void);
+
+/* Number of kernel launches issued through this library by the calling
+ * process so far (all entry points).  bench.py reports the difference over the
+ * timed region as "gpu_launches". */
+uint64_t    fp_launch_count(void);
+
+/*
+ * fp_gene_detected_mean -- mu_g = sum_c x[g,c]*(1-z[g,c]) / sum_c (1-z[g,c]),
+ * NaN -> 0.  Replaces SigScoreMethods.py:109-111 (imputed_eval_signature); the
+ * row sums reproduce NumPy's pairwise summation order bit-for-bit.
+ * out_mu: G float64.
+ */
+int fp_gene_detected_mean(const double *X, const double *Z,
+                          int64_t G, int64_t N, int64_t ld,
+                          double *out_mu, void *stream);
+
+/*
+ * fp_score_signatures -- evaluate K signatures on N cells in one launch
+ * (real and random-background signatures together).
+ * Replaces the per-signature bodies of naive/weighted/imputed/nonzero
+ * _eval_signature (SigScoreMethods.py:34-41, 66-75, 101-121, 147-155) and the
+ * Python loop of calculate_sig_scores (Signatures.py:669-679).
+ * Sums run in ascending gene order with separately rounded multiply and add,
+ * so the result is bit-identical to the reference's NumPy float64 evaluation.
+ *   W        : required for WEIGHTED and IMPUTED, else may be NULL
+ *   Z        : required for IMPUTED and NONZERO, else may be NULL
+ *   gene_mu  : required for IMPUTED (from fp_gene_detected_mean), else NULL
+ *   out_scores : K x ld_out float64
+ * Signatures with zero matched genes must be filtered by the caller (the
+ * reference raises ValueError for them, SigScoreMethods.py:60-64).
+ */
+int fp_score_signatures(int method,
+                        const double *X, const double *W, const double *Z,
+                        int64_t G, int64_t N, int64_t ld,
+                        const int32_t *sig_ptr, const int32_t *sig_gene,
+                        const int8_t *sig_sign, int64_t K,
+                        const double *gene_mu,
+                        double *out_scores, int64_t ld_out, void *stream);
+
+/*
+ * fp_rank_columns -- average ranks (1-based, ties share the mean rank) of each
+ * signature's N scores.  Replaces SignatureScores.ranks =
+ * scipy.stats.rankdata(scores, "average") (SigScoreMethods.py:170-178) and
+ * the matrix assembly of Signatures.py:359-369.
+ *   scores, out_ranks : K x ld float64 (may not alias)
+ */
+size_t fp_rank_workspace_bytes(int64_t K, int64_t N, int64_t ld);
+int fp_rank_columns(const double *scores, int64_t K, int64_t N, int64_t ld,
+                    double *out_ranks, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+/*
+ * fp_consistency -- for one projection, the local dissimilarity
+ *   D[k,i] = | r[k,i] - sum_j w_ij r[k,j] / sum_j w_ij |,
+ *   w_ij = exp(-|p_i - p_j|^2 / sigma_sq_i), w_ii = 0, (sum_j w_ij == 0 -> 1)
+ * without materialising the N x N kernel matrix.  Replaces Signatures.py:396-408
+ * and :412-413 (cdist, exp, zeroed diagonal, row normalisation, both np.dot
+ * calls and the |actual - predicted| step) for real and random signatures in
+ * one call.
+ *   coords       : 2 x N float64 (x row then y row)
+ *   sigma_sq     : per-cell bandwidth^2 (N float64) or NULL to use sigma_sq_scalar
+ *                  (the reference has a single NEIGHBORHOOD_SIZE**2, :398)
+ *   ranks        : K x ld float64
+ *   out_dissim   : K x ld_out float64
+ *   output_kind  : FP_OUT_*  (the factor branch, :493-508, needs the raw prediction)
+ *   precision_mode : FP_PRECISION_*
+ */
+size_t fp_consistency_workspace_bytes(int64_t N, int64_t K, int precision_mode);
+int fp_consistency(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                   const double *ranks, int64_t N, int64_t K, int64_t ld,
+                   double *out_dissim, int64_t ld_out, int output_kind, int precision_mode,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * fp_row_medians -- exact median over the N entries of each of K rows
+ * (mean of the two middle order statistics when N is even; NaN if the row
+ * holds a NaN).  Replaces np.median(dissimilarity, axis=0), Signatures.py:409,414.
+ * Any finite or infinite doubles are accepted (total order on the bit patterns).
+ */
+int fp_row_medians(const double *values, int64_t K, int64_t N, int64_t ld,
+                   double *out_median, void *stream);
+
+/*
+ * fp_background_pvalues -- per-numGenes background N(mu, sigma) from the random
+ * signatures' medians (population std, ddof = 0, NumPy pairwise summation
+ * order) and p = Phi((med - mu) / sigma) for each real signature.
+ * Replaces Signatures.py:417-442.  Grouping / nearest-group matching depends
+ * only on numGenes and is prepared on the host:
+ *   rnd_order[R]         random-signature indices, grouped (group-major, original
+ *                        order inside a group)
+ *   group_ptr[n_groups+1] extents of each group inside rnd_order
+ *   sig_group[K]         for each real signature, the index of its group
+ *   out_p[K], out_mu[n_groups], out_sigma[n_groups]
+ */
+int fp_background_pvalues(const double *med, const int32_t *sig_group, int64_t K,
+                          const double *rnd_med, const int32_t *rnd_order,
+                          const int32_t *group_ptr, int64_t n_groups,
+                          double *out_p, double *out_mu, double *out_sigma,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTPROJECT_B200_H */

@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI and the Python mirror of the
+reference API) with the oracle and with golden vectors produced by the live
+reference.  Bit-exact for scores and ranks; 1e-9 relative for consistency
+values in FP64 mode (BLAS summation order is not reproducible), 1e-6 relative
+is the north-star tolerance."""
+import io
+import contextlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import fp_oracle as O
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["case_synth_odd", "case_synth_even", "case_fixture"]
+CONS_RTOL = 1e-9       # FP64 mode, measured << this; north-star tolerance is 1e-6
+LOGQ_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def fp():
+    import __graft_entry__ as ge
+    ge.build()
+    from fastproject_b200 import Signatures, SigScoreMethods, synth, _engine
+    import types
+    return types.SimpleNamespace(S=Signatures, M=SigScoreMethods, synth=synth, E=_engine)
+
+
+def _data(fp, c):
+    return fp.synth.ExpressionMatrix(c["X"], c["W"], [str(g) for g in c["genes"]],
+                                     [str(x) for x in c["cells"]])
+
+
+# ------------------------------------------------------------------ scoring
+@pytest.mark.parametrize("case_name", CASES)
+@pytest.mark.parametrize("method", G.METHODS)
+def test_scores_and_ranks_bit_exact_vs_reference_golden(fp, case_name, method):
+    c = G.load(case_name)
+    data = _data(fp, c)
+    for tag in ["real", "rnd"] + (["rnds"] if "rnds_sig_ptr" in c else []):
+        sigs = G.unpack_sigs(c, tag + "_", fp.S.Signature)
+        res = fp.S.calculate_sig_scores(data, sigs, method, c["Z"], int(c["min_genes"]))
+        names = [str(s) for s in c["%s_%s_names" % (tag, method)]]
+        assert list(res.keys()) == names
+        got = np.array([res[k].scores for k in names]).reshape(len(names), -1)
+        assert np.array_equal(got, c["%s_%s_scores" % (tag, method)]), (tag, method)
+        assert [res[k].numGenes for k in names] == list(c["%s_%s_numgenes" % (tag, method)])
+        ranks = np.array([res[k].ranks for k in names]).reshape(len(names), -1)
+        assert np.array_equal(ranks, c["%s_%s_ranks" % (tag, method)])
+        first = res[names[0]]
+        assert first.isFactor is False and first.isPrecomputed is False
+        assert first.sample_labels == data.col_labels
+
+
+def test_forder_and_bool_zero_mask_inputs(fp):
+    c = G.load("case_synth_odd")
+    data = fp.synth.ExpressionMatrix(np.asfortranarray(c["X"]), np.asfortranarray(c["W"]),
+                                     [str(g) for g in c["genes"]], [str(x) for x in c["cells"]])
+    sigs = G.unpack_sigs(c, "real_", fp.S.Signature)
+    res = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", c["Z"], 5)
+    got = np.array([res[k].scores for k in res])
+    assert np.array_equal(got, c["real_weighted_avg_scores_forder"])
+    res = fp.S.calculate_sig_scores(data, sigs, "only_nonzero", c["Z"].astype(bool), 5)
+    got = np.array([res[k].scores for k in res])
+    assert np.array_equal(got, c["real_only_nonzero_scores"])
+
+
+def test_single_signature_evaluators_and_errors(fp):
+    c = G.load("case_synth_even")
+    data = _data(fp, c)
+    sigs = G.unpack_sigs(c, "real_", fp.S.Signature)
+    fns = {"naive": fp.M.naive_eval_signature, "weighted_avg": fp.M.weighted_eval_signature,
+           "imputed": fp.M.imputed_eval_signature, "only_nonzero": fp.M.nonzero_eval_signature}
+    for m, fn in fns.items():
+        names = [str(s) for s in c["real_%s_names" % m]]
+        ss = fn(data, sigs[0], c["Z"], 5)
+        k = names.index(sigs[0].name)
+        assert np.array_equal(ss.scores, c["real_%s_scores" % m][k])
+        assert ss.numGenes == c["real_%s_numgenes" % m][k] and ss.name == sigs[0].name
+        small = [s for s in sigs if s.name == "TOO_SMALL"][0]
+        with pytest.raises(ValueError, match="Too few genes match signature"):
+            fn(data, small, c["Z"], 5)
+        nomatch = [s for s in sigs if s.name == "NO_MATCH"][0]
+        with pytest.raises(ValueError, match="No genes match signature"):
+            fn(data, nomatch, c["Z"], 0)
+    # function default min_signature_genes=1e99 discards everything (Signatures.py:631)
+    assert fp.S.calculate_sig_scores(data, sigs) == {}
+    with pytest.raises(UnboundLocalError):
+        fp.S.calculate_sig_scores(data, sigs, "bogus", c["Z"], 0)
+
+
+def test_scores_bit_exact_vs_oracle_midsize(fp):
+    x, w, z, genes, cells = fp.synth.make_expression(1500, 2100, seed=31)
+    w[:, 17] = 0.0                                            # zero normaliser for every signature
+    data = fp.synth.ExpressionMatrix(x, w, genes, cells)
+    random.seed(5); np.random.seed(5)
+    sigs = fp.S.generate_random_sigs(genes, True, [5, 10, 50, 200], 40)
+    odata = O.ExpressionMatrix(x, w, genes, cells)
+    osigs = [O.Signature(s.sig_dict, s.signed, s.source, s.name) for s in sigs]
+    for m in G.METHODS:
+        got = fp.S.calculate_sig_scores(data, sigs, m, z, 5)
+        want = O.calculate_sig_scores(odata, osigs, m, z, 5)
+        assert list(got.keys()) == list(want.keys())
+        a = np.array([got[k].scores for k in want])
+        b = np.array([want[k].scores for k in want])
+        assert np.array_equal(a, b), m
+        assert np.array_equal(np.array([got[k].ranks for k in want]),
+                              np.array([want[k].ranks for k in want])), m
+
+
+def test_rank_ties_constant_negative_zero_and_nan(fp):
+    from scipy.stats import rankdata
+    rng = np.random.RandomState(0)
+    rows = [np.round(rng.normal(size=1001), 1), np.ones(1001), rng.normal(size=1001),
+            np.r_[0.0, -0.0, 0.0, rng.normal(size=998)], rng.randint(0, 5, size=1001).astype(float)]
+    for v in rows:
+        assert np.array_equal(fp.M.SignatureScores(v, "v", [], False, True, 0).ranks,
+                              rankdata(v, method="average"))
+    v = rng.normal(size=77); v[5] = np.nan
+    assert np.isnan(fp.M.SignatureScores(v, "v", [], False, True, 0).ranks).all()
+    with pytest.raises(Exception, match="Factor signature scores have no rank"):
+        fp.M.SignatureScores(["a"], "f", [], True, True, 0).ranks
+
+
+# ------------------------------------------------------------------ kernels through the engine
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 65, 1000, 4097])
+def test_row_medians_exact(fp, n):
+    import torch
+    rng = np.random.RandomState(n)
+    rows = np.vstack([np.abs(rng.normal(size=n)), rng.normal(size=n) * 1e3,
+                      rng.randint(0, 3, size=n).astype(float), np.zeros(n),
+                      np.r_[rng.uniform(size=n - 1), np.inf][:n] if n > 1 else np.ones(1)])
+    ld = fp.E.padded(n)
+    dev = torch.zeros((rows.shape[0], ld), dtype=torch.float64, device="cuda")
+    dev[:, :n] = torch.from_numpy(rows).cuda()
+    got = fp.E.row_medians(dev, n).cpu().numpy()
+    assert np.array_equal(got, np.median(rows, axis=1))
+    if n > 2:
+        rows[1, n // 2] = np.nan
+        dev[:, :n] = torch.from_numpy(rows).cuda()
+        got = fp.E.row_medians(dev, n).cpu().numpy()
+        assert np.isnan(got[1]) and np.array_equal(got[[0, 2, 3]], np.median(rows[[0, 2, 3]], axis=1))
+
+
+def test_background_pvalues_vs_oracle(fp):
+    import torch
+    rng = np.random.RandomState(9)
+    rnd_ng = [int(v) for v in np.repeat([5, 10, 20, 50, 100, 200], 500)]
+    rng.shuffle(rnd_ng)
+    rmed = rng.normal(loc=500, scale=4, size=len(rnd_ng))
+    real_ng = [int(v) for v in rng.randint(1, 300, size=64)]
+    med = rng.normal(loc=470, scale=30, size=64)
+    table = O.background_table(rmed, rnd_ng)
+    want = O.background_pvalues(med, real_ng, table)
+    order, ptr, grp = fp.S._background_groups(rnd_ng, real_ng)
+    t = lambda a, dt: torch.from_numpy(np.asarray(a)).to("cuda", dt)
+    p, mu, sd = fp.E.background_pvalues(t(med, torch.float64), t(grp, torch.int32), t(rmed, torch.float64),
+                                        t(order, torch.int32), t(ptr, torch.int32))
+    assert np.array_equal(mu.cpu().numpy(), table[:, 1])      # NumPy pairwise order reproduced
+    assert np.array_equal(sd.cpu().numpy(), table[:, 2])
+    np.testing.assert_allclose(p.cpu().numpy(), want, rtol=1e-12, atol=0)
+
+
+# ------------------------------------------------------------------ consistency
+def _svp(fp, c, extra=None, **kw):
+    data = _data(fp, c)
+    real = fp.S.calculate_sig_scores(data, G.unpack_sigs(c, "real_", fp.S.Signature), "weighted_avg",
+                                     c["Z"], int(c["min_genes"]))
+    rnd = fp.S.calculate_sig_scores(data, G.unpack_sigs(c, "rnd_", fp.S.Signature), "weighted_avg",
+                                    c["Z"], int(c["min_genes"]))
+    if extra:
+        real.update(extra)
+    return fp.S.sigs_vs_projections(G.projections(c), real, rnd, **kw)
+
+
+def _check_svp(out, c, tag, rtol=CONS_RTOL):
+    rows, cols, cons, logq, rcons, rkeys = out
+    assert rows == [str(s) for s in c[tag + "_rows"]]
+    assert cols == [str(s) for s in c[tag + "_cols"]]
+    assert rkeys == [str(s) for s in c[tag + "_rkeys"]]
+    np.testing.assert_allclose(cons, c[tag + "_cons"], rtol=rtol, atol=0)
+    np.testing.assert_allclose(rcons, c[tag + "_rcons"], rtol=rtol, atol=0)
+    np.testing.assert_allclose(logq, c[tag + "_logq"], rtol=LOGQ_RTOL, atol=1e-9)
+    # identical ranking of the signature x projection pairs and significance calls
+    assert np.array_equal(np.argsort(logq, axis=None, kind="stable"),
+                          np.argsort(c[tag + "_logq"], axis=None, kind="stable"))
+    assert np.array_equal(logq < -1.3, c[tag + "_logq"] < -1.3)
+
+
+@pytest.mark.parametrize("case_name", CASES)
+def test_sigs_vs_projections_vs_reference_golden(fp, case_name):
+    c = G.load(case_name)
+    _check_svp(_svp(fp, c), c, "svp")
+    if "svp_wide_cons" in c:
+        _check_svp(_svp(fp, c, NEIGHBORHOOD_SIZE=0.8), c, "svp_wide")
+
+
+def test_precomputed_numeric_and_factor_branches(fp):
+    c = G.load("case_synth_odd")
+    cells = [str(x) for x in c["cells"]]
+    pre = dict()
+    for name in [str(s) for s in c["pre_names"]]:
+        v = c["pre_" + name]
+        is_factor = v.dtype.kind in "USi"
+        vals = v if not is_factor else ([int(x) for x in v] if v.dtype.kind == "i" else [str(x) for x in v])
+        pre[name] = fp.M.SignatureScores(vals, name, cells, is_factor, True, 0)
+    fp.S._bg_dist = np.zeros((0, 0))
+    _check_svp(_svp(fp, c, extra=pre), c, "svpmix")
+
+
+def test_per_cell_sigma_extension_reduces_to_scalar(fp):
+    c = G.load("case_synth_even")
+    n = c["X"].shape[1]
+    out = _svp(fp, c, sigma_per_cell=np.full(n, 0.33))
+    _check_svp(out, c, "svp")
+
+
+def test_sigs_vs_projections_midsize_vs_oracle(fp):
+    n, g = 3001, 800
+    proj, grad = fp.synth.make_projections(n, 3, seed=21)
+    x, w, z, genes, cells = fp.synth.make_expression(g, n, seed=22, planted=grad)
+    data = fp.synth.ExpressionMatrix(x, w, genes, cells)
+    defs = fp.synth.make_signature_dicts(genes, 40, seed=23)
+    sigs = [fp.S.Signature(d, sg, "t", nm) for nm, d, sg in defs]
+    random.seed(8); np.random.seed(8)
+    rnd = fp.S.generate_random_sigs(genes, False, [5, 10, 20, 50, 100, 200], 50)
+    real = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", z, 5)
+    bg = fp.S.calculate_sig_scores(data, rnd, "weighted_avg", z, 5)
+    got = fp.S.sigs_vs_projections(proj, real, bg)
+    odata = O.ExpressionMatrix(x, w, genes, cells)
+    oreal = O.calculate_sig_scores(odata, [O.Signature(s.sig_dict, s.signed, "t", s.name) for s in sigs],
+                                   "weighted_avg", z, 5)
+    obg = O.calculate_sig_scores(odata, [O.Signature(s.sig_dict, s.signed, "t", s.name) for s in rnd],
+                                 "weighted_avg", z, 5)
+    want = O.sigs_vs_projections(proj, oreal, obg)
+    assert got[0] == want[0] and got[1] == want[1] and got[5] == want[5]
+    np.testing.assert_allclose(got[2], want[2], rtol=CONS_RTOL)
+    np.testing.assert_allclose(got[4], want[4], rtol=CONS_RTOL)
+    np.testing.assert_allclose(got[3], want[3], rtol=LOGQ_RTOL, atol=1e-9)
+    assert np.array_equal(np.argsort(got[3], axis=None, kind="stable"),
+                          np.argsort(want[3], axis=None, kind="stable"))
+    assert np.array_equal(got[3] < -1.3, want[3] < -1.3)
+    assert (want[3] < -1.3).any() and not (want[3] < -1.3).all()
+
+
+def test_smoke_entry_point():
+    import __graft_entry__ as ge
+    with contextlib.redirect_stdout(io.StringIO()):
+        ge.smoke()
