@@ -207,7 +207,11 @@ def run_b200(args):
     d_sign = E.to_device(sig_sign, torch.int8)
     proj_names = sorted(wl["projections"].keys())
     coords = [E.to_device(wl["projections"][p]) for p in proj_names]
-    order, gptr, grp = S._background_groups(list(counts[n_real:]), list(counts[:n_real]))
+    # who owns what: [n_real, n_rows] of every rank, and every row's numGenes
+    shape_all = D.all_gather_counts([n_real, n_rows], device=device).reshape(world, 2)
+    counts_all = D.all_gather_counts(counts, device=device)
+    bg = D.GlobalBackground(counts_all, [int(v) for v in shape_all[:, 0]],
+                            [int(v) for v in shape_all[:, 1]], device)
     ld = E.padded(N)
     dissim = torch.empty((n_rows, ld), dtype=torch.float64, device=device)
     sig2 = SIGMA ** 2
@@ -233,8 +237,8 @@ def run_b200(args):
                 cons_ev.append((c0, c1))
             meds.append(E.row_medians(dissim, N))
         med = torch.stack(meds)                               # [P x rows]
-        all_med = D.all_gather_medians(med) if world > 1 else med
-        return D.pvalues_from_medians(all_med, n_real, n_rows, world, order, gptr, grp, device)
+        all_med = D.all_gather_rows(med)                      # the only exchange: P x rows doubles
+        return bg.pvalues(all_med), all_med
 
     def sync():
         if world > 1:
@@ -265,7 +269,7 @@ def run_b200(args):
     score_ms = sum(a.elapsed_time(b) for a, b in score_ev) / max(1, len(score_ev))
     cons_ms = sum(a.elapsed_time(b) for a, b in cons_ev) / max(1, len(cons_ev))
 
-    pairs = n_rows * P * world
+    pairs = int(shape_all[:, 1].sum()) * P
     value = pairs / (ms_step * 1e-3)
     peaks = measured_peaks()
     cons_flops = 2.0 * N * N * (n_rows + 1)                   # per launch (one projection)
@@ -299,8 +303,8 @@ def run_b200(args):
         "roofline": roofline, "roofline_scoring": roofline_score,
         "clocks": clocks,
     }
-    checksum = float(out[0].sum()) if out is not None else 0.0
-    result["checksum_p"] = checksum
+    result["checksum_p"] = float(out[0].sum())
+    result["checksum_median"] = float(out[1].sum())
 
     if rank == 0 and world == 1 and not args.no_e2e:
         result["e2e"] = run_e2e(args, cfg, wl, precision)
