@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FP_BENCH_WORKLOAD", "C2"))
-    ap.add_argument("--precision", default=None, help="fp64 | tf32x3 (default: library default)")
+    ap.add_argument("--precision", default=None, help="fp64 | tc (default: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -192,7 +192,7 @@ def run_b200(args):
     from fastproject_b200 import Signatures as S, _engine as E, _native, _scoring, synth, distributed as D
 
     cfg = WORKLOADS[args.workload]
-    precision = args.precision or E.default_precision()
+    precision = E.resolve_precision(args.precision, cfg["N"])
     # weak scaling: every rank owns its own block of K real + R random signatures
     wl = make_workload(cfg, device, seed=1335607828 + 7919 * rank)
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
@@ -290,7 +290,7 @@ def run_b200(args):
                   "consistency + median + p-values)",
         "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if precision == "fp64" else "tf32x3+f64",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if precision == "fp64" else "i8 digit planes (tcgen05) + f64",
         "data": "synthetic",
         "config": {"workload": "%s: %d cells x %d genes, %d real + %d random signatures per GPU, "
                                "%d projections, sigma=0.33" % (args.workload, N, G, n_real,

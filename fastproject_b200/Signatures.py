@@ -202,7 +202,7 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     :param sig_scores_dict: dict of (string) => SignatureScores
     :param random_sig_scores_dict: dict of (string) => SignatureScores (background)
     :param NEIGHBORHOOD_SIZE: Gaussian kernel bandwidth (scalar, as in the reference)
-    :param precision: (extension) "fp64" | "tf32x3"; default from
+    :param precision: (extension) "fp64" | "tc"; default from
         FASTPROJECT_B200_PRECISION, else "fp64"
     :param sigma_per_cell: (extension) optional (N,) array of per-cell bandwidths
         replacing NEIGHBORHOOD_SIZE

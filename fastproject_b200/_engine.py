@@ -35,8 +35,19 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+TC_MAX_CELLS = 32640     # FP_PRECISION_TC: two balanced base-256 digits of 2*rank - (N+1)
+
+
 def default_precision():
-    return os.environ.get("FASTPROJECT_B200_PRECISION", "fp64")
+    return os.environ.get("FASTPROJECT_B200_PRECISION", "auto")
+
+
+def resolve_precision(precision, n):
+    """"auto": the tensor-core path when the shape is supported, else FP64."""
+    precision = precision or default_precision()
+    if precision == "auto":
+        return "tc" if n <= TC_MAX_CELLS else "fp64"
+    return precision
 
 
 # --------------------------------------------------------------------------
@@ -117,6 +128,7 @@ expression_cache = _ExpressionCache()
 
 def clear_device_cache():
     expression_cache.clear()
+    _ws_cache.clear()
 
 
 # --------------------------------------------------------------------------
@@ -158,14 +170,33 @@ def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_AB
     k, ld = ranks.shape
     if out is None:
         out = torch.empty((k, ld), dtype=torch.float64, device=ranks.device)
-    mode = _native.PRECISION_CODES[precision or default_precision()]
+    mode = _native.PRECISION_CODES[resolve_precision(precision, n)]
     vec = sigma_sq if isinstance(sigma_sq, torch.Tensor) else None
     scalar = 0.0 if vec is not None else float(sigma_sq)
     nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=ranks.device) if nbytes else None
+    ws, ws_ptr = _workspace(nbytes, ranks.device)
     _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
-                 ptr(out), out.stride(0), output_kind, mode, ptr(ws), nbytes, stream_ptr())
+                 ptr(out), out.stride(0), output_kind, mode, ws_ptr, nbytes, stream_ptr())
     return out
+
+
+_WS_ALIGN = 1024
+_ws_cache = dict()
+
+
+def _workspace(nbytes, device):
+    """Scratch buffer for one call (1024-byte aligned: the TMA / UMMA tiles of
+    the tensor-core path need it).  The largest buffer per device is kept and
+    reused; all work of a process goes to one stream at a time."""
+    if not nbytes:
+        return None, 0
+    key = str(device)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes + _WS_ALIGN:
+        buf = torch.empty((nbytes + _WS_ALIGN,), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    base = buf.data_ptr()
+    return buf, (base + _WS_ALIGN - 1) // _WS_ALIGN * _WS_ALIGN
 
 
 def row_medians(values, n):

@@ -11,6 +11,11 @@ int fp_consistency_fp64(const double *coords, const double *sigma_sq, double sig
                         const double *ranks, int64_t N, int64_t K, int64_t ld, double *out_dissim,
                         int64_t ld_out, int output_kind, cudaStream_t st);
 
+size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K);
+int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                      const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
+                      int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
 namespace fp {
 
 static thread_local char g_error[512] = "";
@@ -46,9 +51,7 @@ extern "C" const char *fp_last_error(void) { return fp::g_error; }
 extern "C" uint64_t fp_launch_count(void) { return fp::g_launches.load(); }
 
 extern "C" size_t fp_consistency_workspace_bytes(int64_t N, int64_t K, int precision_mode) {
-    (void)N;
-    (void)K;
-    if (precision_mode == FP_PRECISION_FP64) return 0;
+    if (precision_mode == FP_PRECISION_TC) return fp_consistency_tc_workspace_bytes(N, K);
     return 0;
 }
 
@@ -57,8 +60,6 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
                               double *out_dissim, int64_t ld_out, int output_kind,
                               int precision_mode, void *workspace, size_t workspace_bytes, void *stream) {
     fp::clear_error();
-    (void)workspace;
-    (void)workspace_bytes;
     FP_CHECK_ARG(coords && ranks && out_dissim, "fp_consistency: null pointer");
     FP_CHECK_ARG(N > 0 && K >= 0 && ld >= N && ld_out >= N,
                  "fp_consistency: bad shape N=%ld K=%ld ld=%ld ld_out=%ld", (long)N, (long)K, (long)ld,
@@ -70,6 +71,9 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
     if (precision_mode == FP_PRECISION_FP64)
         return fp_consistency_fp64(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim,
                                    ld_out, output_kind, fp::as_stream(stream));
-    fp::set_error("fp_consistency: precision mode %d not built", precision_mode);
+    if (precision_mode == FP_PRECISION_TC)
+        return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim, ld_out,
+                                 output_kind, workspace, workspace_bytes, fp::as_stream(stream));
+    fp::set_error("fp_consistency: unknown precision mode %d", precision_mode);
     return FP_EUNSUPPORTED;
 }

@@ -1,0 +1,581 @@
+// Signature x projection local dissimilarity on the Blackwell tensor cores.
+//
+// Replaces, for one projection, /root/reference/FastProject/Signatures.py:396-408
+// and :412-413 (cdist -> exp(-d^2/sigma^2) -> zero diagonal -> row normalise ->
+// np.dot(weights, rank matrix) -> |rank - prediction|) for real and random
+// signatures together, WITHOUT materialising the N x N kernel matrix.
+//
+// Arithmetic (FP_PRECISION_TC): an error-free digit-sliced contraction on
+// tcgen05.mma kind::i8 (s32 accumulators in tensor memory -- integer
+// accumulation is exact, so no tensor-core rounding enters the result):
+//
+//   prediction_i = sum_j w_ij v_j / sum_j w_ij,  w_ij = exp(-(d_ij^2 - m_i)/sigma_i^2)
+//
+//   * m_i = min_{j != i} d_ij^2 (nearest neighbour): a per-row scale that cancels
+//     in the quotient and puts the largest weight of every row at exactly 1;
+//   * W_ij = round(w_ij * (2^32 - 1)) is a 32-bit fixed-point weight, generated
+//     on the fly in FP64 (table + cubic for 2^t, |error| < 2^-33) by the CUDA
+//     cores of the CTA that consumes it and written straight into shared
+//     memory as four unsigned 8-bit digit planes (the UMMA B operand);
+//   * the values are half-integers (average ranks, one-hot / binary columns), so
+//     r_j = 2 v_j - (N + 1) is an integer; it is cut into balanced signed base-256
+//     digits (planes of s8, the UMMA A operand, loaded by TMA, 128-byte swizzle);
+//   * every (weight digit, value digit) plane pair is one MMA; pairs of equal
+//     weight 256^(4-c) share an s32 accumulator ("class" c); sum_j W_ij r_j is
+//     rebuilt exactly in int64 in the epilogue.  The lowest class (2^-32 relative,
+//     below the weight quantisation) is not computed;
+//   * the normaliser sum_j W_ij comes from the same MMAs through a row of ones
+//     appended to every block of 127 signatures, so numerator and denominator
+//     use identical quantised weights (the quotient is an exact weighted mean
+//     with weights perturbed by < 2^-33 relative to the row maximum).
+//
+// Tile: 128 signature rows (M) x 128 cells (N) per CTA, j streamed in stages of
+// 128; 4 classes x 128 columns = all 512 TMEM columns.  Warp roles: warp 0 TMA
+// producer, warp 1 MMA issuer (one elected lane), warps 2-9 weight generators,
+// then epilogue.  The FP64 verifier lives in consistency_fp64.cu.
+#include "fp_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace fp::tc;
+
+constexpr int TM = 128;            // signature rows per tile (127 + the ones row)
+constexpr int SIGS_PER_TILE = 127;
+constexpr int TN = 128;            // cells i per tile
+constexpr int KS = 128;            // cells j per stage (bytes of K per digit plane)
+constexpr int WD = 4;              // weight digits (32-bit fixed point)
+constexpr int STAGES = 2;
+constexpr int GEN_WARPS = 8;
+constexpr int GEN_THREADS = GEN_WARPS * 32;
+constexpr int THREADS = 64 + GEN_THREADS;
+constexpr int PLANE_BYTES = 128 * KS;   // 16 KB: one digit plane of one operand, one stage
+constexpr int NCLASS = 4;
+constexpr int TAB = 256;           // 2^(k/256) table
+
+template <int SR>
+struct SmemLayout {
+    static constexpr int stage_bytes = (SR + WD) * PLANE_BYTES;
+    static constexpr int table_off = STAGES * stage_bytes;
+    static constexpr int den_off = table_off + TAB * 8;
+    static constexpr int bar_off = den_off + TN * 8;
+    static constexpr int total = bar_off + 128;
+};
+
+// cell records prepared by cell_setup_kernel
+struct __align__(32) CellI { double alpha, c, x2c, y2c; };   // row side
+struct __align__(32) CellJ { double x, y, nb, pad; };         // column side
+
+// ---------------------------------------------------------------------------
+// per-cell set-up: nearest-neighbour distance (row scale) and the coefficients
+// of t_ij = log2(e)/sigma_i^2 * (m_i - d_ij^2) = alpha_i + c_i*nb_j + X_i*x_j + Y_i*y_j
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ sigma_sq,
+                  double sigma_sq_scalar, long N, long Npad, CellI *__restrict__ ci, CellJ *__restrict__ cj) {
+    __shared__ double sx[256], sy[256];
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    const double *cx = coords, *cy = coords + N;
+    const bool live = i < N;
+    const double xi = live ? cx[i] : 0.0, yi = live ? cy[i] : 0.0;
+    double m = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    for (long j0 = 0; j0 < N; j0 += 256) {
+        const long jj = j0 + threadIdx.x;
+        sx[threadIdx.x] = jj < N ? cx[jj] : 0.0;
+        sy[threadIdx.x] = jj < N ? cy[jj] : 0.0;
+        __syncthreads();
+        const int lim = (int)((N - j0) < 256 ? (N - j0) : 256);
+        for (int t = 0; t < lim; ++t) {
+            const double dx = xi - sx[t], dy = yi - sy[t];
+            const double d2 = fma(dx, dx, dy * dy);
+            if (j0 + t != i && d2 < m) m = d2;
+        }
+        __syncthreads();
+    }
+    if (i >= Npad) return;
+    const double s2 = sigma_sq ? (live ? sigma_sq[i] : 1.0) : sigma_sq_scalar;
+    const double c = 1.4426950408889634074 / s2;             // log2(e) / sigma^2
+    CellI a;
+    a.c = c;
+    a.x2c = 2.0 * c * xi;
+    a.y2c = 2.0 * c * yi;
+    // a row whose largest weight underflows to 0 in the reference (or that has no
+    // other cell) has row sum 0 -> prediction 0 (Signatures.py:400-402)
+    const bool dead = !live || !(m < __longlong_as_double(0x7ff0000000000000LL)) || exp(-m / s2) == 0.0;
+    a.alpha = dead ? __longlong_as_double(0xfff0000000000000LL) : c * (m - fma(xi, xi, yi * yi));
+    ci[i] = a;
+    CellJ b;
+    b.x = xi;
+    b.y = yi;
+    b.nb = live ? -fma(xi, xi, yi * yi) : __longlong_as_double(0xfff0000000000000LL);
+    b.pad = 0.0;
+    cj[i] = b;
+}
+
+// ---------------------------------------------------------------------------
+// value range -> centre and power-of-two scale of the digit representation.
+// r = (2 v - centre2) * 2^shift is an integer whose top digit is always well
+// used: for average ranks centre2 = N + 1; for one-hot / binary columns
+// r = +-2^14, so the full 32-bit weight meets the only non-zero digit.
+// range[0] = ordered key of min(v), range[1] = ordered key of max(v).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_key(unsigned long long key) {
+    const unsigned long long u = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void __launch_bounds__(256)
+value_range_kernel(const double *__restrict__ values, long K, long N, long ld,
+                   unsigned long long *__restrict__ range) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    bool nan = false;
+    for (long row = blockIdx.y; row < K; row += gridDim.y)
+        for (long j = (long)blockIdx.x * 256 + threadIdx.x; j < N; j += (long)gridDim.x * 256) {
+            const double v = values[row * ld + j];
+            nan |= (v != v);
+            const unsigned long long k = ordered_key(v);
+            lo = k < lo ? k : lo;
+            hi = k > hi ? k : hi;
+        }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, off);
+        const unsigned long long h2 = __shfl_xor_sync(0xffffffffu, hi, off);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&range[0], lo);
+        atomicMax(&range[1], hi);
+    }
+    if (nan) atomicMax(&range[2], 1ull);
+}
+
+struct Digits {
+    double centre2;   // integer valued
+    double scale;     // 2^shift
+    bool valid;
+};
+template <int SR>
+__device__ __forceinline__ Digits decode_range(const unsigned long long *__restrict__ range) {
+    constexpr double LIMIT = SR == 2 ? 32639.0 : 8355711.0;   // 127 * (256^SR - 1) / 255
+    const double mn2 = 2.0 * from_ordered_key(range[0]), mx2 = 2.0 * from_ordered_key(range[1]);
+    Digits d;
+    d.centre2 = floor(0.5 * (mn2 + mx2));
+    const double hr = fmax(mx2 - d.centre2, d.centre2 - mn2);
+    d.valid = range[2] == 0ull && hr <= LIMIT;               // false for NaN / inf / too wide
+    d.scale = 1.0;
+    for (int it = 0; it < 24 && 2.0 * d.scale * hr <= LIMIT && hr > 0.0; ++it) d.scale *= 2.0;
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// values -> balanced base-256 digit planes of r = (2 v - centre2) * scale, blocked as the
+// A operand wants: plane b, tile row R = 128*blk + r holds signature 127*blk + r
+// (r < 127) and the ones row (r = 127: most significant digit 1, others 0).
+// planes[b][R][j], j padded with zeros to Npad.  Sets *flag if a value is not a
+// half-integer or r does not fit SR digits.
+// ---------------------------------------------------------------------------
+template <int SR>
+__global__ void __launch_bounds__(256)
+pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, long Kpad, long Npad,
+                   int8_t *__restrict__ planes, const unsigned long long *__restrict__ range,
+                   int *__restrict__ flag) {
+    const Digits dg = decode_range<SR>(range);
+    const long R = blockIdx.y;
+    const long j4 = ((long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (j4 >= Npad) return;
+    const long blk = R / TM, r = R % TM;
+    const long sig = blk * SIGS_PER_TILE + r;
+    uint32_t word[SR];
+#pragma unroll
+    for (int b = 0; b < SR; ++b) word[b] = 0;
+    bool bad = !dg.valid;
+    if (r == TM - 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (j4 + e < N) word[0] |= 1u << (8 * e);
+    } else if (sig < K) {
+        constexpr long LIMIT = SR == 2 ? 32639 : 8355711;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (j4 + e >= N) continue;
+            const double v2 = (2.0 * values[sig * ld + j4 + e] - dg.centre2) * dg.scale;
+            long q = (long)v2;
+            if ((double)q != v2 || q > LIMIT || q < -LIMIT) {
+                bad = true;
+                q = 0;
+            }
+#pragma unroll
+            for (int b = SR - 1; b >= 0; --b) {
+                const long lo = ((q + 128) & 255) - 128;       // balanced digit in [-128, 127]
+                q = (q - lo) >> 8;
+                word[b] |= (uint32_t)(lo & 255) << (8 * e);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < SR; ++b)
+        *reinterpret_cast<uint32_t *>(planes + ((long)b * Kpad + R) * Npad + j4) = word[b];
+    if (bad) atomicOr(flag, 1);
+}
+
+// ---------------------------------------------------------------------------
+// 2^t * (2^32 - 1), t <= 0, rounded to nearest: the fixed-point weight
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t weight_fixed32(double t, const double *__restrict__ tab) {
+    constexpr double MAGIC = 26388279066624.0;              // 1.5 * 2^44: ulp = 2^-8
+    constexpr double L1 = 0.69314718055994530942, L2 = 0.24022650695910071233, L3 = 0.05550410866482157995;
+    const bool ok = t > -40.0;                              // below: W < 2^-8 ulp -> 0 (also -inf / NaN)
+    const double z = t + MAGIC;
+    const int ti = __double2loint(z);                       // round(256 t), two's complement
+    const double g = t - (z - MAGIC);                       // |g| <= 2^-9
+    const double p = g * fma(g, fma(g, L3, L2), L1);        // 2^g - 1
+    const double T = tab[ti & (TAB - 1)];                   // 2^(k/256) * (2^32 - 1)
+    const double v = fma(T, p, T);
+    const int q = ti >> 8;                                  // floor(t) <= 0
+    const double vs = __hiloint2double(__double2hiint(v) + q * (1 << 20), __double2loint(v));
+    const uint32_t w = (uint32_t)__double2loint(vs + 4503599627370496.0);   // + 2^52: round to integer
+    return ok ? (ti > 0 ? 0xffffffffu : w) : 0u;
+}
+
+template <int SR>
+__global__ void __launch_bounds__(THREADS, 1)
+consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const CellI *__restrict__ ci,
+                      const CellJ *__restrict__ cj, const double *__restrict__ values, long ld,
+                      double *__restrict__ out, long ld_out, long N, long K, long Kpad, int n_stages,
+                      int output_kind, const unsigned long long *__restrict__ range,
+                      const int *__restrict__ flag) {
+    using L = SmemLayout<SR>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is 1024-aligned by the launch (128-byte swizzle needs it)
+    uint8_t *smem = smem_raw;
+    double *tab = reinterpret_cast<double *>(smem + L::table_off);
+    double *den_s = reinterpret_cast<double *>(smem + L::den_off);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES]
+    uint64_t *empty = full + STAGES;                                             // [STAGES]
+    uint64_t *accum_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long i0 = (long)blockIdx.x * TN;
+    const long blk = blockIdx.y;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1 + GEN_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_planes);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid >= 64) {
+        const int g = tid - 64;                              // 256 generator threads fill the table
+        tab[g] = exp2((double)g * (1.0 / TAB)) * 4294967295.0;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (value digit planes)
+        if (lane == 0) {
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], SR * PLANE_BYTES);
+                uint8_t *dst = smem + s * L::stage_bytes;
+#pragma unroll
+                for (int b = 0; b < SR; ++b)
+                    tma_load_2d(dst + b * PLANE_BYTES, &tmap_planes, it * KS, (int)(b * Kpad + blk * TM), &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        const uint32_t idesc = idesc_i8(TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
+        for (int it = 0; it < n_stages; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(smem + s * L::stage_bytes);
+                const uint32_t b_base = a_base + SR * PLANE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < KS / 32; ++ks) {
+                    uint64_t ad[SR], bd[WD];
+#pragma unroll
+                    for (int b = 0; b < SR; ++b)
+                        ad[b] = smem_desc(a_base + b * PLANE_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+                    for (int a = 0; a < WD; ++a)
+                        bd[a] = smem_desc(b_base + a * PLANE_BYTES + ks * 2 * TN * 16, TN * 16, 128, LAYOUT_NONE);
+                    const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+                    // class c = (weight digit a) + (value digit b), value digit 0 = most significant
+#pragma unroll
+                    for (int a = 0; a < WD; ++a)
+#pragma unroll
+                        for (int b = 0; b < SR; ++b) {
+                            const int c = a + b;
+                            if (c >= NCLASS) continue;
+                            // the first product written to a class overwrites: (a=0,b=c) for c < SR, else (a=c-SR+1,b=SR-1)
+                            const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
+                            umma_i8(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
+                        }
+                }
+                umma_commit(&empty[s]);                      // frees the stage when these MMAs are done
+                if (it == n_stages - 1) umma_commit(accum_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------ weight generators (B operand)
+        const int g = tid - 64;
+        const int cell = g & (TN - 1), jhalf = g >> 7;
+        const long gi = i0 + cell;
+        const CellI me = ci[gi];
+        for (int it = 0; it < n_stages; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t *bst = smem + s * L::stage_bytes + SR * PLANE_BYTES;
+            const long jbase = (long)it * KS + jhalf * 64;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const long jj = jbase + c * 16 + e;
+                    const double2 xy = __ldg(reinterpret_cast<const double2 *>(cj + jj));
+                    const double nb = __ldg(reinterpret_cast<const double *>(cj + jj) + 2);
+                    double t = fma(me.c, nb, me.alpha);
+                    t = fma(me.x2c, xy.x, t);
+                    t = fma(me.y2c, xy.y, t);
+                    const uint32_t wv = weight_fixed32(t, tab);
+                    w[e] = (jj == gi) ? 0u : wv;            // weights[diag] = 0 (Signatures.py:399)
+                }
+                const int chunk = jhalf * 4 + c;
+#pragma unroll
+                for (int a = 0; a < WD; ++a) {
+                    const uint32_t sel = (3 - a) * 0x11 + 0x40;   // byte (3-a) of x, byte (3-a) of y
+                    uint4 v;
+                    v.x = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+                    v.y = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
+                    v.z = __byte_perm(__byte_perm(w[8], w[9], sel), __byte_perm(w[10], w[11], sel), 0x5410);
+                    v.w = __byte_perm(__byte_perm(w[12], w[13], sel), __byte_perm(w[14], w[15], sel), 0x5410);
+                    *reinterpret_cast<uint4 *>(bst + a * PLANE_BYTES + (chunk * TN + cell) * 16) = v;
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+
+        // ------------------------------------------------ epilogue
+        mbar_wait(accum_full, 0);
+        tc_fence_after_sync();
+        const int quad = warp & 3;                           // TMEM lanes 32*quad .. +31
+        const int half = (warp - 2) >> 2;                    // columns 64*half .. +63
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const bool invalid = *flag != 0;
+        // phase A: the ones row (tile row 127) gives sum_j W_ij * 256
+        if (quad == 3) {
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int col0 = half * 64 + b * 16;
+                uint32_t acc[NCLASS][16];
+#pragma unroll
+                for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                tmem_ld_wait();
+                if (lane == 31) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        long long d = 0;
+#pragma unroll
+                        for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - c));
+                        den_s[col0 + e] = (double)d * (1.0 / 256.0);
+                    }
+                }
+            }
+        }
+        named_barrier_sync(1, GEN_THREADS);
+        const int row = quad * 32 + lane;
+        const long sig = blk * SIGS_PER_TILE + row;
+        const bool row_live = row < SIGS_PER_TILE && sig < K;
+        const Digits dg = decode_range<SR>(range);
+        const double centre = dg.centre2, inv_scale = 1.0 / dg.scale;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            const int col0 = half * 64 + b * 16;
+            uint32_t acc[NCLASS][16];
+#pragma unroll
+            for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+            tmem_ld_wait();
+            if (row_live) {
+                double res[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    long long num = 0;
+#pragma unroll
+                    for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - c));
+                    const double den = den_s[col0 + e];
+                    // num = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
+                    // zero row sum -> prediction 0 (:400-402)
+                    res[e] = den > 0.0 ? 0.5 * (((double)num / den) * inv_scale + centre) : 0.0;
+                }
+                const long ibase = i0 + col0;
+                double *orow = out + sig * ld_out + ibase;
+                const double *vrow = values + sig * ld + ibase;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    if (ibase + e < N) {
+                        double r = res[e];
+                        if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
+                        if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
+                        orow[e] = r;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+    int sr;
+    long nblk, Kpad, Npad;
+    size_t planes_off, ci_off, cj_off, flag_off, range_off, total;
+};
+
+bool make_plan(long N, long K, Plan *p) {
+    if (N > 32640) return false;                 // two value digits; three digits + j chunking: not built yet
+    p->sr = 2;
+    p->nblk = (K + SIGS_PER_TILE - 1) / SIGS_PER_TILE;
+    p->Kpad = p->nblk * TM;
+    p->Npad = (long)align_up((size_t)N, KS);
+    size_t off = 0;
+    p->planes_off = off;
+    off += align_up((size_t)p->sr * p->Kpad * p->Npad, 1024);
+    p->ci_off = off;
+    off += align_up((size_t)p->Npad * sizeof(CellI), 1024);
+    p->cj_off = off;
+    off += align_up((size_t)p->Npad * sizeof(CellJ), 1024);
+    p->flag_off = off;
+    p->range_off = off + 64;
+    off += 1024;
+    p->total = off;
+    return true;
+}
+
+}  // namespace
+
+size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K) {
+    Plan p;
+    if (N <= 0 || K <= 0 || !make_plan(N, K, &p)) return 0;
+    return p.total;
+}
+
+int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                      const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
+                      int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    Plan p;
+    if (!make_plan(N, K, &p)) {
+        fp::set_error("fp_consistency: FP_PRECISION_TC supports N <= 32640 cells in this build (N=%ld)", (long)N);
+        return FP_EUNSUPPORTED;
+    }
+    if (!workspace || workspace_bytes < p.total) {
+        fp::set_error("fp_consistency: workspace %zu bytes < required %zu", workspace_bytes, p.total);
+        return FP_EWORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
+        fp::set_error("fp_consistency: workspace must be 1024-byte aligned");
+        return FP_EINVAL;
+    }
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        fp::set_error("fp_consistency: cuTensorMapEncodeTiled not available from the driver");
+        return FP_ECUDA;
+    }
+    char *ws = static_cast<char *>(workspace);
+    int8_t *planes = reinterpret_cast<int8_t *>(ws + p.planes_off);
+    CellI *ci = reinterpret_cast<CellI *>(ws + p.ci_off);
+    CellJ *cj = reinterpret_cast<CellJ *>(ws + p.cj_off);
+    int *flag = reinterpret_cast<int *>(ws + p.flag_off);
+
+    unsigned long long *range = reinterpret_cast<unsigned long long *>(ws + p.range_off);
+    FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
+    FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
+    FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
+    {
+        unsigned gy = (unsigned)(K < 4096 ? K : 4096);
+        unsigned gx = (unsigned)((N + 255) / 256);
+        if (gx > 32) gx = 32;
+        value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
+        FP_CHECK_LAUNCH("value_range_kernel");
+    }
+    cell_setup_kernel<<<(unsigned)(p.Npad / 256 + 1), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N, p.Npad,
+                                                                   ci, cj);
+    FP_CHECK_LAUNCH("cell_setup_kernel");
+    {
+        dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
+        pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
+        FP_CHECK_LAUNCH("pack_values_kernel");
+    }
+    CUtensorMap tmap;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.Npad, (cuuint64_t)(p.sr * p.Kpad)};
+        cuuint64_t strides[1] = {(cuuint64_t)p.Npad};
+        cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)TM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fp::set_error("fp_consistency: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return FP_ECUDA;
+        }
+    }
+    using L = SmemLayout<2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           L::total));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)p.nblk);
+    consistency_tc_kernel<2><<<grid, THREADS, L::total, st>>>(tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad,
+                                                              (int)(p.Npad / KS), output_kind, range, flag);
+    FP_CHECK_LAUNCH("consistency_tc_kernel");
+    return FP_OK;
+}

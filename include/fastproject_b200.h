@@ -66,7 +66,7 @@ extern "C" {
 
 /* arithmetic of the neighbourhood contraction in fp_consistency */
 #define FP_PRECISION_FP64      0   /* float64 FMA on the FP64 pipe (verifier)           */
-#define FP_PRECISION_TF32X3    1   /* tcgen05 kind::tf32, hi/lo split, FP64 promotion   */
+#define FP_PRECISION_TC        1   /* tcgen05 kind::i8: exact digit-sliced contraction   */
 
 int         fp_abi_version(void);
 const char *fp_version(void);

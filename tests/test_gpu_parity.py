@@ -17,7 +17,13 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["case_synth_odd", "case_synth_even", "case_fixture"]
 CONS_RTOL = 1e-9       # FP64 mode, measured << this; north-star tolerance is 1e-6
+TC_CONS_RTOL = 2e-8    # tensor-core mode (exact digit-sliced int8 contraction, 32-bit fixed-point weights)
 LOGQ_RTOL = 1e-6
+PRECISIONS = ["fp64", "tc"]
+
+
+def _rtol(precision):
+    return CONS_RTOL if precision == "fp64" else TC_CONS_RTOL
 
 
 @pytest.fixture(scope="module")
@@ -190,15 +196,18 @@ def _check_svp(out, c, tag, rtol=CONS_RTOL):
     assert np.array_equal(logq < -1.3, c[tag + "_logq"] < -1.3)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case_name", CASES)
-def test_sigs_vs_projections_vs_reference_golden(fp, case_name):
+def test_sigs_vs_projections_vs_reference_golden(fp, case_name, precision):
     c = G.load(case_name)
-    _check_svp(_svp(fp, c), c, "svp")
+    _check_svp(_svp(fp, c, precision=precision), c, "svp", rtol=_rtol(precision))
     if "svp_wide_cons" in c:
-        _check_svp(_svp(fp, c, NEIGHBORHOOD_SIZE=0.8), c, "svp_wide")
+        _check_svp(_svp(fp, c, NEIGHBORHOOD_SIZE=0.8, precision=precision), c, "svp_wide",
+                   rtol=_rtol(precision))
 
 
-def test_precomputed_numeric_and_factor_branches(fp):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_precomputed_numeric_and_factor_branches(fp, precision):
     c = G.load("case_synth_odd")
     cells = [str(x) for x in c["cells"]]
     pre = dict()
@@ -208,17 +217,82 @@ def test_precomputed_numeric_and_factor_branches(fp):
         vals = v if not is_factor else ([int(x) for x in v] if v.dtype.kind == "i" else [str(x) for x in v])
         pre[name] = fp.M.SignatureScores(vals, name, cells, is_factor, True, 0)
     fp.S._bg_dist = np.zeros((0, 0))
-    _check_svp(_svp(fp, c, extra=pre), c, "svpmix")
+    _check_svp(_svp(fp, c, extra=pre, precision=precision), c, "svpmix", rtol=_rtol(precision))
 
 
-def test_per_cell_sigma_extension_reduces_to_scalar(fp):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_per_cell_sigma_extension_reduces_to_scalar(fp, precision):
     c = G.load("case_synth_even")
     n = c["X"].shape[1]
-    out = _svp(fp, c, sigma_per_cell=np.full(n, 0.33))
-    _check_svp(out, c, "svp")
+    out = _svp(fp, c, sigma_per_cell=np.full(n, 0.33), precision=precision)
+    _check_svp(out, c, "svp", rtol=_rtol(precision))
 
 
-def test_sigs_vs_projections_midsize_vs_oracle(fp):
+def _tc_case(fp, n, k, seed, outliers=0, dup=0, per_cell=False, binary=False, kind=0):
+    """Same inputs through the FP64 verifier kernel and the tensor-core kernel."""
+    import torch
+    from scipy.stats import rankdata
+    rng = np.random.RandomState(seed)
+    proj, _ = fp.synth.make_projections(n, 1, seed=seed)
+    coords = proj["Proj00"].copy()
+    for o in range(outliers):
+        coords[:, o] = [6.0 + 3 * o, -5.0 - o]
+    for d in range(dup):
+        coords[:, n - 1 - d] = coords[:, d + 5]
+    if binary:
+        vals = (rng.uniform(size=(k, n)) < 0.3).astype(np.float64)
+    else:
+        vals = np.array([rankdata(rng.normal(size=n) + (coords[0] if r % 3 == 0 else 0)) for r in range(k)])
+        vals[k - 1] = rankdata(np.round(rng.normal(size=n), 1))      # many ties -> half-integer ranks
+    ld = fp.E.padded(n)
+    dev = torch.zeros((k, ld), dtype=torch.float64, device="cuda")
+    dev[:, :n] = torch.from_numpy(vals).cuda()
+    c = torch.from_numpy(coords).cuda()
+    sig = 0.33 ** 2
+    if per_cell:
+        sig = torch.from_numpy((0.2 + 0.3 * rng.uniform(size=n)) ** 2).cuda()
+    a = fp.E.consistency(c, sig, dev, n, precision="fp64", output_kind=kind)[:, :n].cpu().numpy()
+    b = fp.E.consistency(c, sig, dev, n, precision="tc", output_kind=kind)[:, :n].cpu().numpy()
+    return a, b
+
+
+@pytest.mark.parametrize("n,k,kw", [
+    (1, 2, {}), (2, 3, {}), (127, 1, {}), (129, 127, {}), (300, 128, dict(dup=3)),
+    (1000, 5, dict(outliers=2)), (4097, 260, dict(outliers=2, dup=3)), (2000, 40, dict(per_cell=True)),
+])
+def test_tensor_core_kernel_matches_fp64_kernel(fp, n, k, kw):
+    a, b = _tc_case(fp, n, k, 31 + n, **kw)
+    assert not np.isnan(b).any()
+    # absolute error of the prediction, in rank units, relative to the rank range
+    assert np.abs(a - b).max() <= 1e-7 * max(n, 16)
+    np.testing.assert_allclose(np.median(b, axis=1), np.median(a, axis=1), rtol=0, atol=1e-8 * max(n, 16))
+
+
+def test_tensor_core_kernel_binary_predictions(fp):
+    a, b = _tc_case(fp, 2000, 300, 5, binary=True, kind=1)
+    assert np.abs(a - b).max() <= 1e-8          # values in [0, 1]: the scale puts +-1 in the top digit
+
+
+def test_tensor_core_kernel_rejects_what_it_cannot_represent(fp):
+    import torch
+    from fastproject_b200 import _native
+    n, k = 500, 3
+    ld = fp.E.padded(n)
+    proj, _ = fp.synth.make_projections(n, 1, seed=3)
+    c = torch.from_numpy(proj["Proj00"]).cuda()
+    vals = torch.zeros((k, ld), dtype=torch.float64, device="cuda")
+    vals[:, :n] = torch.rand((k, n), dtype=torch.float64, device="cuda")      # not half-integers
+    out = fp.E.consistency(c, 0.33 ** 2, vals, n, precision="tc")
+    assert torch.isnan(out[:, :n]).all()                                      # loud, not silently wrong
+    big = fp.E.TC_MAX_CELLS + 1
+    with pytest.raises(_native.NativeError):
+        fp.E.consistency(torch.zeros((2, big), dtype=torch.float64, device="cuda"), 0.1,
+                         torch.zeros((1, fp.E.padded(big)), dtype=torch.float64, device="cuda"), big,
+                         precision="tc")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_sigs_vs_projections_midsize_vs_oracle(fp, precision):
     n, g = 3001, 800
     proj, grad = fp.synth.make_projections(n, 3, seed=21)
     x, w, z, genes, cells = fp.synth.make_expression(g, n, seed=22, planted=grad)
@@ -229,7 +303,7 @@ def test_sigs_vs_projections_midsize_vs_oracle(fp):
     rnd = fp.S.generate_random_sigs(genes, False, [5, 10, 20, 50, 100, 200], 50)
     real = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", z, 5)
     bg = fp.S.calculate_sig_scores(data, rnd, "weighted_avg", z, 5)
-    got = fp.S.sigs_vs_projections(proj, real, bg)
+    got = fp.S.sigs_vs_projections(proj, real, bg, precision=precision)
     odata = O.ExpressionMatrix(x, w, genes, cells)
     oreal = O.calculate_sig_scores(odata, [O.Signature(s.sig_dict, s.signed, "t", s.name) for s in sigs],
                                    "weighted_avg", z, 5)
@@ -237,8 +311,8 @@ def test_sigs_vs_projections_midsize_vs_oracle(fp):
                                  "weighted_avg", z, 5)
     want = O.sigs_vs_projections(proj, oreal, obg)
     assert got[0] == want[0] and got[1] == want[1] and got[5] == want[5]
-    np.testing.assert_allclose(got[2], want[2], rtol=CONS_RTOL)
-    np.testing.assert_allclose(got[4], want[4], rtol=CONS_RTOL)
+    np.testing.assert_allclose(got[2], want[2], rtol=_rtol(precision))
+    np.testing.assert_allclose(got[4], want[4], rtol=_rtol(precision))
     np.testing.assert_allclose(got[3], want[3], rtol=LOGQ_RTOL, atol=1e-9)
     assert np.array_equal(np.argsort(got[3], axis=None, kind="stable"),
                           np.argsort(want[3], axis=None, kind="stable"))
