@@ -33,6 +33,8 @@
 // 128; 4 classes x 128 columns = all 512 TMEM columns.  Warp roles: warp 0 TMA
 // producer, warp 1 MMA issuer (one elected lane), warps 2-9 weight generators,
 // then epilogue.  The FP64 verifier lives in consistency_fp64.cu.
+#include <stdlib.h>
+
 #include "fp_common.cuh"
 #include "tc_common.cuh"
 
@@ -46,18 +48,24 @@ constexpr int TN = 128;            // cells i per tile
 constexpr int KS = 128;            // cells j per stage (bytes of K per digit plane)
 constexpr int WD = 4;              // weight digits (32-bit fixed point)
 constexpr int STAGES = 2;
-constexpr int GEN_WARPS = 8;
+constexpr int GEN_WARPS = 16;
 constexpr int GEN_THREADS = GEN_WARPS * 32;
 constexpr int THREADS = 64 + GEN_THREADS;
 constexpr int PLANE_BYTES = 128 * KS;   // 16 KB: one digit plane of one operand, one stage
 constexpr int NCLASS = 4;
-constexpr int TAB = 256;           // 2^(k/256) table
+constexpr int TAB = 128;           // 2^(k/128) table ...
+constexpr int TAB_COPIES = 16;     // ... one copy per lane of a half-warp: LDS.64 without bank conflicts
+constexpr int CELLS_PER_LANE = 2;     // two generator warps share one 16-byte K chunk (64 cells each)
+// padding / dead rows use a large finite exponent instead of -inf so that the
+// integer part of t always fits the 32-bit extraction in weight_fixed32
+constexpr double T_DEAD = -1.0e6;
 
 template <int SR>
 struct SmemLayout {
     static constexpr int stage_bytes = (SR + WD) * PLANE_BYTES;
     static constexpr int table_off = STAGES * stage_bytes;
-    static constexpr int den_off = table_off + TAB * 8;
+    static constexpr int jrec_off = table_off + TAB * TAB_COPIES * 8;       // per generator warp: 16 CellJ
+    static constexpr int den_off = jrec_off + GEN_WARPS * 16 * 32;
     static constexpr int bar_off = den_off + TN * 8;
     static constexpr int total = bar_off + 128;
 };
@@ -102,12 +110,14 @@ cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ 
     // a row whose largest weight underflows to 0 in the reference (or that has no
     // other cell) has row sum 0 -> prediction 0 (Signatures.py:400-402)
     const bool dead = !live || !(m < __longlong_as_double(0x7ff0000000000000LL)) || exp(-m / s2) == 0.0;
-    a.alpha = dead ? __longlong_as_double(0xfff0000000000000LL) : c * (m - fma(xi, xi, yi * yi));
+    // - 2^-30: keeps t_ij <= 0 against the rounding of the expanded form (a common row
+    // factor 2^(-2^-30), cancels in the quotient)
+    a.alpha = dead ? T_DEAD : c * (m - fma(xi, xi, yi * yi)) - 9.313225746154785e-10;
     ci[i] = a;
     CellJ b;
     b.x = xi;
     b.y = yi;
-    b.nb = live ? -fma(xi, xi, yi * yi) : __longlong_as_double(0xfff0000000000000LL);
+    b.nb = live ? -fma(xi, xi, yi * yi) : T_DEAD;            // c * nb <= -1e6 * log2(e) / sigma^2
     b.pad = 0.0;
     cj[i] = b;
 }
@@ -224,22 +234,26 @@ pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, l
 }
 
 // ---------------------------------------------------------------------------
-// 2^t * (2^32 - 1), t <= 0, rounded to nearest: the fixed-point weight
+// 2^t * (2^32 - 1), t <= 0, rounded to nearest: the fixed-point weight.
+// t = n + k/128 + g (|g| <= 2^-8): table for 2^(k/128), cubic for 2^g - 1
+// (remainder < 2^-40), exponent n added to the exponent field, + 2^52 rounds to
+// an integer.  tab points at this lane's copy of the table (stride TAB_COPIES).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t weight_fixed32(double t, const double *__restrict__ tab) {
-    constexpr double MAGIC = 26388279066624.0;              // 1.5 * 2^44: ulp = 2^-8
+    constexpr double MAGIC = 52776558133248.0;              // 1.5 * 2^45: ulp = 2^-7
     constexpr double L1 = 0.69314718055994530942, L2 = 0.24022650695910071233, L3 = 0.05550410866482157995;
-    const bool ok = t > -40.0;                              // below: W < 2^-8 ulp -> 0 (also -inf / NaN)
+    // t > -40 <=> high word below that of -40.0 (sign bit set, larger magnitude = larger word)
+    const bool ok = (uint32_t)__double2hiint(t) < 0xC0440000u;
     const double z = t + MAGIC;
-    const int ti = __double2loint(z);                       // round(256 t), two's complement
-    const double g = t - (z - MAGIC);                       // |g| <= 2^-9
+    const int ti = __double2loint(z);                       // round(128 t), two's complement
+    const double g = t - (z - MAGIC);                       // |g| <= 2^-8
     const double p = g * fma(g, fma(g, L3, L2), L1);        // 2^g - 1
-    const double T = tab[ti & (TAB - 1)];                   // 2^(k/256) * (2^32 - 1)
+    const double T = tab[(ti & (TAB - 1)) * TAB_COPIES];    // 2^(k/128) * (2^32 - 1)
     const double v = fma(T, p, T);
-    const int q = ti >> 8;                                  // floor(t) <= 0
-    const double vs = __hiloint2double(__double2hiint(v) + q * (1 << 20), __double2loint(v));
+    const int q = ti >> 7;                                  // floor(t) <= 0
+    const double vs = __hiloint2double(__double2hiint(v) + (q << 20), __double2loint(v));
     const uint32_t w = (uint32_t)__double2loint(vs + 4503599627370496.0);   // + 2^52: round to integer
-    return ok ? (ti > 0 ? 0xffffffffu : w) : 0u;
+    return ok ? w : 0u;
 }
 
 template <int SR>
@@ -248,7 +262,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                       const CellJ *__restrict__ cj, const double *__restrict__ values, long ld,
                       double *__restrict__ out, long ld_out, long N, long K, long Kpad, int n_stages,
                       int output_kind, const unsigned long long *__restrict__ range,
-                      const int *__restrict__ flag) {
+                      const int *__restrict__ flag, int dbg) {
     using L = SmemLayout<SR>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is 1024-aligned by the launch (128-byte swizzle needs it)
@@ -275,8 +289,9 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid >= 64) {
-        const int g = tid - 64;                              // 256 generator threads fill the table
-        tab[g] = exp2((double)g * (1.0 / TAB)) * 4294967295.0;
+        // 256 generator threads fill the 16 copies of the table
+        for (int idx = tid - 64; idx < TAB * TAB_COPIES; idx += GEN_THREADS)
+            tab[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -327,7 +342,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                             if (c >= NCLASS) continue;
                             // the first product written to a class overwrites: (a=0,b=c) for c < SR, else (a=c-SR+1,b=SR-1)
                             const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
-                            umma_i8(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
+                            if (!(dbg & 1)) umma_i8(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
                         }
                 }
                 umma_commit(&empty[s]);                      // frees the stage when these MMAs are done
@@ -337,39 +352,76 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         }
     } else {
         // ------------------------------------------------ weight generators (B operand)
-        const int g = tid - 64;
-        const int cell = g & (TN - 1), jhalf = g >> 7;
-        const long gi = i0 + cell;
-        const CellI me = ci[gi];
+        // generator warps 2w, 2w+1 own the 16-byte K chunk w of every stage (16 cells j):
+        // one the cells 0-63 of the tile, the other 64-127; lane l produces the weights of
+        // two cells, so the (x_j, y_j, -|p_j|^2) record of a j is fetched once per two weights.
+        const int chunk = (warp - 2) >> 1;
+        const int cell0 = ((warp - 2) & 1) * 64 + lane;
+        const double *my_tab = tab + (lane & (TAB_COPIES - 1));
+        CellI me[CELLS_PER_LANE];
+#pragma unroll
+        for (int cc = 0; cc < CELLS_PER_LANE; ++cc) me[cc] = ci[i0 + cell0 + 32 * cc];
+        // the 16 column records of this warp's chunk go through a private 512-byte slot of
+        // shared memory (broadcast reads); the next stage's records are prefetched into
+        // registers by lanes 0-15 while this stage is computed (L2 latency hidden)
+        CellJ *jslot = reinterpret_cast<CellJ *>(smem + L::jrec_off) + (warp - 2) * 16;
+        const CellJ *jsrc = cj + chunk * 16 + (lane & 15);
+        uint4 pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc));
+        uint4 pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc) + 1);
         for (int it = 0; it < n_stages; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
+            const long jbase = (long)it * KS + chunk * 16;
+            __syncwarp();
+            if (lane < 16) {
+                reinterpret_cast<uint4 *>(jslot + lane)[0] = pre0;
+                reinterpret_cast<uint4 *>(jslot + lane)[1] = pre1;
+            }
+            __syncwarp();
+            if (it + 1 < n_stages) {
+                pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS));
+                pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS) + 1);
+            }
+            uint32_t w[CELLS_PER_LANE][16];
+            if (dbg & 2) {
+#pragma unroll
+                for (int cc = 0; cc < CELLS_PER_LANE; ++cc)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) w[cc][e] = 0x01020304u * (e + cc + it);
+            } else
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const double2 xy = *reinterpret_cast<const double2 *>(jslot + e);
+                const double nb = jslot[e].nb;
+#pragma unroll
+                for (int cc = 0; cc < CELLS_PER_LANE; ++cc) {
+                    double t = fma(me[cc].c, nb, me[cc].alpha);
+                    t = fma(me[cc].x2c, xy.x, t);
+                    t = fma(me[cc].y2c, xy.y, t);
+                    w[cc][e] = weight_fixed32(t, my_tab);
+                }
+            }
+            // weights[diag] = 0 (Signatures.py:399): at most one chunk of one stage per cell
+            if (jbase < i0 + TN && jbase + 16 > i0) {
+#pragma unroll
+                for (int cc = 0; cc < CELLS_PER_LANE; ++cc)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (jbase + e == i0 + cell0 + 32 * cc) w[cc][e] = 0u;
+            }
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t *bst = smem + s * L::stage_bytes + SR * PLANE_BYTES;
-            const long jbase = (long)it * KS + jhalf * 64;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t w[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const long jj = jbase + c * 16 + e;
-                    const double2 xy = __ldg(reinterpret_cast<const double2 *>(cj + jj));
-                    const double nb = __ldg(reinterpret_cast<const double *>(cj + jj) + 2);
-                    double t = fma(me.c, nb, me.alpha);
-                    t = fma(me.x2c, xy.x, t);
-                    t = fma(me.y2c, xy.y, t);
-                    const uint32_t wv = weight_fixed32(t, tab);
-                    w[e] = (jj == gi) ? 0u : wv;            // weights[diag] = 0 (Signatures.py:399)
-                }
-                const int chunk = jhalf * 4 + c;
+            for (int cc = 0; cc < CELLS_PER_LANE; ++cc) {
+                const int cell = cell0 + 32 * cc;
 #pragma unroll
                 for (int a = 0; a < WD; ++a) {
                     const uint32_t sel = (3 - a) * 0x11 + 0x40;   // byte (3-a) of x, byte (3-a) of y
                     uint4 v;
-                    v.x = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
-                    v.y = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
-                    v.z = __byte_perm(__byte_perm(w[8], w[9], sel), __byte_perm(w[10], w[11], sel), 0x5410);
-                    v.w = __byte_perm(__byte_perm(w[12], w[13], sel), __byte_perm(w[14], w[15], sel), 0x5410);
+                    v.x = __byte_perm(__byte_perm(w[cc][0], w[cc][1], sel), __byte_perm(w[cc][2], w[cc][3], sel), 0x5410);
+                    v.y = __byte_perm(__byte_perm(w[cc][4], w[cc][5], sel), __byte_perm(w[cc][6], w[cc][7], sel), 0x5410);
+                    v.z = __byte_perm(__byte_perm(w[cc][8], w[cc][9], sel), __byte_perm(w[cc][10], w[cc][11], sel), 0x5410);
+                    v.w = __byte_perm(__byte_perm(w[cc][12], w[cc][13], sel), __byte_perm(w[cc][14], w[cc][15], sel), 0x5410);
                     *reinterpret_cast<uint4 *>(bst + a * PLANE_BYTES + (chunk * TN + cell) * 16) = v;
                 }
             }
@@ -382,14 +434,15 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         mbar_wait(accum_full, 0);
         tc_fence_after_sync();
         const int quad = warp & 3;                           // TMEM lanes 32*quad .. +31
-        const int half = (warp - 2) >> 2;                    // columns 64*half .. +63
+        const int part = (warp - 2) >> 2;                    // columns COLS_PER_WARP*part .. (4 warps per quadrant)
+        constexpr int COLS_PER_WARP = TN / (GEN_WARPS / 4);
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const bool invalid = *flag != 0;
         // phase A: the ones row (tile row 127) gives sum_j W_ij * 256
         if (quad == 3) {
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int col0 = half * 64 + b * 16;
+            for (int b = 0; b < COLS_PER_WARP / 16; ++b) {
+                const int col0 = part * COLS_PER_WARP + b * 16;
                 uint32_t acc[NCLASS][16];
 #pragma unroll
                 for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
@@ -412,8 +465,8 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         const Digits dg = decode_range<SR>(range);
         const double centre = dg.centre2, inv_scale = 1.0 / dg.scale;
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
-            const int col0 = half * 64 + b * 16;
+        for (int b = 0; b < COLS_PER_WARP / 16; ++b) {
+            const int col0 = part * COLS_PER_WARP + b * 16;
             uint32_t acc[NCLASS][16];
 #pragma unroll
             for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
@@ -538,9 +591,9 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
     FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
     FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
     {
-        unsigned gy = (unsigned)(K < 4096 ? K : 4096);
-        unsigned gx = (unsigned)((N + 255) / 256);
-        if (gx > 32) gx = 32;
+        unsigned gy = (unsigned)(K < 296 ? K : 296);
+        unsigned gx = (unsigned)((N + 2047) / 2048);
+        if (gx > 4) gx = 4;
         value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
         FP_CHECK_LAUNCH("value_range_kernel");
     }
@@ -575,7 +628,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
     }
     dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)p.nblk);
     consistency_tc_kernel<2><<<grid, THREADS, L::total, st>>>(tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad,
-                                                              (int)(p.Npad / KS), output_kind, range, flag);
+                                                              (int)(p.Npad / KS), output_kind, range, flag, getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0);
     FP_CHECK_LAUNCH("consistency_tc_kernel");
     return FP_OK;
 }

@@ -1,0 +1,197 @@
+// Throughput probe for the FP64 pipe and for the fixed-point weight generator
+// of consistency_tc.cu on B200.  Stand-alone:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_rate_probe fp64_rate_probe.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s line %d\n", cudaGetErrorString(e_), __LINE__); return 2; } } while (0)
+
+template <int ILP>
+__global__ void dfma_kernel(double *out, int iters, double a, double b) {
+    double v[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) v[k] = threadIdx.x + k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) v[k] = fma(v[k], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += v[k];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <int ILP>
+__global__ void dadd_kernel(double *out, int iters, double a) {
+    double v[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) v[k] = threadIdx.x + k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) v[k] = v[k] + a;
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += v[k];
+    if (s == 12345.678) out[0] = s;
+}
+
+constexpr int TAB = 128, TAB_COPIES = 16;
+template <int VAR>
+__device__ __forceinline__ uint32_t weight_fixed32(double t, const double *__restrict__ tab) {
+    if (VAR == 5) return (uint32_t)__double2loint(t);
+    constexpr double MAGIC = 52776558133248.0;
+    constexpr double L1 = 0.69314718055994530942, L2 = 0.24022650695910071233, L3 = 0.05550410866482157995;
+    const bool ok = (uint32_t)__double2hiint(t) < 0xC0440000u;
+    const double z = t + MAGIC;
+    const int ti = __double2loint(z);
+    const double g = t - (z - MAGIC);
+    const double p = g * fma(g, fma(g, L3, L2), L1);
+    const double T = VAR == 3 ? 4294967295.0 : tab[(ti & (TAB - 1)) * TAB_COPIES];
+    const double v = fma(T, p, T);
+    const int q = ti >> 7;
+    const double vs = __hiloint2double(__double2hiint(v) + (q << 20), __double2loint(v));
+    const uint32_t w = (uint32_t)__double2loint(vs + 4503599627370496.0);
+    return (VAR == 4 || ok) ? w : 0u;
+}
+
+// each thread: CELLS cells x 16 j per iteration, like the kernel's generator (no smem stores if !STORE)
+template <int CELLS, bool STORE, int VAR, bool JSMEM = false>
+__global__ void __launch_bounds__(512) weight_kernel(const double4 *ci, const double4 *cj, uint32_t *out, int iters) {
+    extern __shared__ double smem[];
+    double *tab = smem;
+    uint4 *planes = reinterpret_cast<uint4 *>(smem + TAB * TAB_COPIES);
+    double4 *js = reinterpret_cast<double4 *>(smem + TAB * TAB_COPIES + 8192);   // 128 records after the planes
+    for (int idx = threadIdx.x; idx < 128; idx += blockDim.x) js[idx] = cj[idx];
+    for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += blockDim.x)
+        tab[idx] = exp2((double)(idx / TAB_COPIES) / TAB) * 4294967295.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *my_tab = tab + (lane & 15);
+    double4 me[CELLS];
+#pragma unroll
+    for (int cc = 0; cc < CELLS; ++cc) me[cc] = ci[(blockIdx.x * 128 + lane + 32 * cc) & 8191];
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t w[CELLS][16];
+        const long jbase = ((long)it * 128 + (warp & 7) * 16) & 8191;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            double2 xy;
+            double nb;
+            if (JSMEM) {
+                const int jl = (int)((jbase + e + it * 37) & 127);
+                xy = *reinterpret_cast<const double2 *>(js + jl);
+                nb = *(reinterpret_cast<const double *>(js + jl) + 2);
+            } else {
+                xy = __ldg(reinterpret_cast<const double2 *>(cj + jbase + e));
+                nb = __ldg(reinterpret_cast<const double *>(cj + jbase + e) + 2);
+            }
+#pragma unroll
+            for (int cc = 0; cc < CELLS; ++cc) {
+                double t = fma(me[cc].y, nb, me[cc].x);
+                t = fma(me[cc].z, xy.x, t);
+                t = fma(me[cc].w, xy.y, t);
+                w[cc][e] = weight_fixed32<VAR>(t, my_tab);
+            }
+        }
+        if (VAR == 2) {
+#pragma unroll
+            for (int cc = 0; cc < CELLS; ++cc)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc ^= w[cc][e];
+        } else
+#pragma unroll
+        for (int cc = 0; cc < CELLS; ++cc) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint32_t sel = (3 - a) * 0x11 + 0x40;
+                uint4 v;
+                v.x = __byte_perm(__byte_perm(w[cc][0], w[cc][1], sel), __byte_perm(w[cc][2], w[cc][3], sel), 0x5410);
+                v.y = __byte_perm(__byte_perm(w[cc][4], w[cc][5], sel), __byte_perm(w[cc][6], w[cc][7], sel), 0x5410);
+                v.z = __byte_perm(__byte_perm(w[cc][8], w[cc][9], sel), __byte_perm(w[cc][10], w[cc][11], sel), 0x5410);
+                v.w = __byte_perm(__byte_perm(w[cc][12], w[cc][13], sel), __byte_perm(w[cc][14], w[cc][15], sel), 0x5410);
+                if (STORE)
+                    planes[(a * 8 + (warp & 7)) * 128 + ((lane + 32 * cc) & 127)] = v;
+                else
+                    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            }
+        }
+    }
+    if (!STORE && acc == 0x12345678u) out[0] = acc;
+    if (STORE && planes[threadIdx.x & 1023].x == 0x12345678u) out[1] = 1;
+}
+
+int main() {
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    double *dout;
+    CK(cudaMalloc(&dout, 64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float ms;
+    const int iters = 20000;
+#define RUN_D(KERN, ILP, THREADS, ...)                                                                  \
+    do {                                                                                                \
+        KERN<ILP><<<sms, THREADS>>>(dout, 100, __VA_ARGS__);                                            \
+        CK(cudaEventRecord(e0));                                                                        \
+        KERN<ILP><<<sms, THREADS>>>(dout, iters, __VA_ARGS__);                                          \
+        CK(cudaEventRecord(e1));                                                                        \
+        CK(cudaDeviceSynchronize());                                                                    \
+        CK(cudaEventElapsedTime(&ms, e0, e1));                                                          \
+        printf("%-12s ILP=%2d threads=%4d: %.2f ops/clk/SM (assuming 1.965 GHz)\n", #KERN, ILP, THREADS, \
+               (double)iters * ILP * THREADS / (ms * 1e-3 * 1.965e9));                                  \
+    } while (0)
+    RUN_D(dfma_kernel, 1, 256, 1.0000001, 1e-9);
+    RUN_D(dfma_kernel, 4, 256, 1.0000001, 1e-9);
+    RUN_D(dfma_kernel, 8, 256, 1.0000001, 1e-9);
+    RUN_D(dfma_kernel, 4, 512, 1.0000001, 1e-9);
+    RUN_D(dfma_kernel, 8, 1024, 1.0000001, 1e-9);
+    RUN_D(dfma_kernel, 1, 1024, 1.0000001, 1e-9);
+    RUN_D(dadd_kernel, 8, 1024, 1e-9);
+    RUN_D(dadd_kernel, 1, 256, 1e-9);
+
+    // weight generator
+    double4 *ci, *cj;
+    CK(cudaMalloc(&ci, 8192 * 32));
+    CK(cudaMalloc(&cj, 8192 * 32));
+    {
+        double4 *h = new double4[8192];
+        for (int i = 0; i < 8192; ++i) {
+            const double x = (i % 97) / 97.0 - 0.5, y = (i % 89) / 89.0 - 0.5, c = 13.25;
+            h[i] = make_double4(-c * (x * x + y * y) - 0.001, c, 2 * c * x, 2 * c * y);
+        }
+        CK(cudaMemcpy(ci, h, 8192 * 32, cudaMemcpyHostToDevice));
+        for (int i = 0; i < 8192; ++i) {
+            const double x = (i % 97) / 97.0 - 0.5, y = (i % 89) / 89.0 - 0.5;
+            h[i] = make_double4(x, y, -(x * x + y * y), 0);
+        }
+        CK(cudaMemcpy(cj, h, 8192 * 32, cudaMemcpyHostToDevice));
+        delete[] h;
+    }
+    const size_t smem = TAB * TAB_COPIES * 8 + 64 * 1024 + 8192;
+#define RUN_W(CELLS, STORE, THREADS, VAR, ...)                                                                          \
+    do {                                                                                                      \
+        CK(cudaFuncSetAttribute(weight_kernel<CELLS, STORE, VAR, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        weight_kernel<CELLS, STORE, VAR, ##__VA_ARGS__><<<sms, THREADS, smem>>>(ci, cj, (uint32_t *)dout, 10);                    \
+        const int wit = 2000;                                                                                 \
+        CK(cudaEventRecord(e0));                                                                              \
+        weight_kernel<CELLS, STORE, VAR, ##__VA_ARGS__><<<sms, THREADS, smem>>>(ci, cj, (uint32_t *)dout, wit);                   \
+        CK(cudaEventRecord(e1));                                                                              \
+        CK(cudaDeviceSynchronize());                                                                          \
+        CK(cudaEventElapsedTime(&ms, e0, e1));                                                                \
+        printf("weights cells/lane=%d store=%d threads=%4d var=%d: %.3f clk/weight/SM\n", CELLS, (int)STORE, THREADS, VAR, \
+               ms * 1e-3 * 1.965e9 / ((double)wit * 16 * CELLS * THREADS));                                   \
+    } while (0)
+    RUN_W(2, true, 512, 1);
+    RUN_W(2, true, 512, 1, true);
+    RUN_W(2, false, 512, 5, true);
+    RUN_W(2, false, 512, 2, true);
+    RUN_W(2, false, 512, 3, true);
+    RUN_W(1, true, 512, 1, true);
+    RUN_W(4, true, 256, 1, true);
+    RUN_W(4, true, 512, 1, true);
+    return 0;
+}
