@@ -35,7 +35,7 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-TC_MAX_CELLS = 32640     # FP_PRECISION_TC: two balanced base-256 digits of 2*rank - (N+1)
+TC_MAX_CELLS = 4000000   # FP_PRECISION_TC: three balanced base-256 digits of the centred values
 
 
 def default_precision():

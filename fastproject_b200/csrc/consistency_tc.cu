@@ -29,10 +29,13 @@
 //     use identical quantised weights (the quotient is an exact weighted mean
 //     with weights perturbed by < 2^-33 relative to the row maximum).
 //
-// Tile: 128 signature rows (M) x 128 cells (N) per CTA, j streamed in stages of
-// 128; 4 classes x 128 columns = all 512 TMEM columns.  Warp roles: warp 0 TMA
-// producer, warp 1 MMA issuer (one elected lane), warps 2-9 weight generators,
-// then epilogue.  The FP64 verifier lives in consistency_fp64.cu.
+// Tile: a PAIR of CTAs (cluster of 2, tcgen05 cta_group::2) owns 2 x 128 signature rows
+// (M = 256) x 128 cells; j is streamed in stages of 128.  Each CTA loads the value planes
+// of its own 128 rows by TMA and GENERATES the weights of 64 of the 128 cells -- the MMA
+// reads the B operand from both CTAs' shared memory, so every generated weight feeds 254
+// signatures.  4 classes x 128 columns = all 512 TMEM columns of each SM.  Warp roles:
+// warp 0 TMA producer, warp 1 MMA issuer (leader CTA, one elected lane), warps 2-17 weight
+// generators, then epilogue.  The FP64 verifier lives in consistency_fp64.cu.
 #include <stdlib.h>
 
 #include "fp_common.cuh"
@@ -42,32 +45,35 @@ namespace {
 
 using namespace fp::tc;
 
-constexpr int TM = 128;            // signature rows per tile (127 + the ones row)
+constexpr int TM = 128;            // signature rows per CTA (127 + the ones row)
 constexpr int SIGS_PER_TILE = 127;
-constexpr int TN = 128;            // cells i per tile
+constexpr int TN = 128;            // cells i per CTA pair
+constexpr int TNH = TN / 2;        // cells whose weights one CTA generates
 constexpr int KS = 128;            // cells j per stage (bytes of K per digit plane)
 constexpr int WD = 4;              // weight digits (32-bit fixed point)
-constexpr int STAGES = 2;
 constexpr int GEN_WARPS = 16;
 constexpr int GEN_THREADS = GEN_WARPS * 32;
 constexpr int THREADS = 64 + GEN_THREADS;
-constexpr int PLANE_BYTES = 128 * KS;   // 16 KB: one digit plane of one operand, one stage
+constexpr int A_PLANE_BYTES = TM * KS;    // 16 KB: one value digit plane, one stage
+constexpr int B_PLANE_BYTES = TNH * KS;   //  8 KB: one weight digit plane of this CTA's 64 cells
 constexpr int NCLASS = 4;
 constexpr int TAB = 128;           // 2^(k/128) table ...
 constexpr int TAB_COPIES = 16;     // ... one copy per lane of a half-warp: LDS.64 without bank conflicts
-constexpr int CELLS_PER_LANE = 2;     // two generator warps share one 16-byte K chunk (64 cells each)
+// s32 accumulators: a class sums at most 3 digit products of magnitude <= 255 * 128 per j
+constexpr int CHUNK_STAGES_3 = 128;       // three value digits: drain every 16 384 cells j
 // padding / dead rows use a large finite exponent instead of -inf so that the
 // integer part of t always fits the 32-bit extraction in weight_fixed32
 constexpr double T_DEAD = -1.0e6;
 
 template <int SR>
 struct SmemLayout {
-    static constexpr int stage_bytes = (SR + WD) * PLANE_BYTES;
-    static constexpr int table_off = STAGES * stage_bytes;
+    static constexpr int stages = SR == 2 ? 3 : 2;
+    static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
+    static constexpr int table_off = stages * stage_bytes;
     static constexpr int jrec_off = table_off + TAB * TAB_COPIES * 8;       // per generator warp: 16 CellJ
     static constexpr int den_off = jrec_off + GEN_WARPS * 16 * 32;
     static constexpr int bar_off = den_off + TN * 8;
-    static constexpr int total = bar_off + 128;
+    static constexpr int total = bar_off + 256;   // 18 mbarriers + the TMEM slot
 };
 
 // cell records prepared by cell_setup_kernel
@@ -257,121 +263,156 @@ __device__ __forceinline__ uint32_t weight_fixed32(double t, const double *__res
 }
 
 template <int SR>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const CellI *__restrict__ ci,
                       const CellJ *__restrict__ cj, const double *__restrict__ values, long ld,
                       double *__restrict__ out, long ld_out, long N, long K, long Kpad, int n_stages,
-                      int output_kind, const unsigned long long *__restrict__ range,
+                      int chunk_stages, int output_kind, const unsigned long long *__restrict__ range,
                       const int *__restrict__ flag, int dbg) {
     using L = SmemLayout<SR>;
+    constexpr int STAGES = L::stages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // dynamic smem is 1024-aligned by the launch (128-byte swizzle needs it)
-    uint8_t *smem = smem_raw;
+    uint8_t *smem = smem_raw;                                 // 1024-aligned (128-byte swizzle atoms)
     double *tab = reinterpret_cast<double *>(smem + L::table_off);
     double *den_s = reinterpret_cast<double *>(smem + L::den_off);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES]
-    uint64_t *empty = full + STAGES;                                             // [STAGES]
-    uint64_t *accum_full = empty + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES] leader's are used
+    uint64_t *empty = full + 4;                                                  // [STAGES] one per CTA
+    uint64_t *bready = empty + 4;                                                // [STAGES] one per CTA
+    uint64_t *accum_full = bready + 4;                                           // one per CTA
+    uint64_t *tmem_empty = accum_full + 1;                                       // leader's is used
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long i0 = (long)blockIdx.x * TN;
-    const long blk = blockIdx.y;
+    const uint32_t rank = cluster_ctarank();                  // 0 = leader of the pair
+    const long i0 = (long)(blockIdx.x >> 1) * TN;             // first cell of the pair's tile
+    const long blk = (long)blockIdx.y * 2 + rank;             // this CTA's block of 127 signatures
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1 + GEN_WARPS);
+            mbar_init(&full[s], 2);                           // leader's TMA thread + the peer's relay warp
             mbar_init(&empty[s], 1);
+            mbar_init(&bready[s], GEN_WARPS);                 // this CTA's generator warps
         }
         mbar_init(accum_full, 1);
+        mbar_init(tmem_empty, 2 * GEN_WARPS);
         mbar_fence_init();
         tma_prefetch_desc(&tmap_planes);
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
     if (tid >= 64) {
-        // 256 generator threads fill the 16 copies of the table
         for (int idx = tid - 64; idx < TAB * TAB_COPIES; idx += GEN_THREADS)
             tab[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
+        if (tid - 64 < TN) den_s[tid - 64] = 0.0;
     }
     tc_fence_before_sync();
-    __syncthreads();
+    cluster_sync();                                           // barriers of both CTAs are initialised
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer (value digit planes)
+        // ------------------------------------------------ TMA producer (value digit planes of this CTA's rows)
         if (lane == 0) {
             for (int it = 0; it < n_stages; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], SR * PLANE_BYTES);
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * SR * A_PLANE_BYTES);
+                const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
                 uint8_t *dst = smem + s * L::stage_bytes;
 #pragma unroll
                 for (int b = 0; b < SR; ++b)
-                    tma_load_2d(dst + b * PLANE_BYTES, &tmap_planes, it * KS, (int)(b * Kpad + blk * TM), &full[s]);
+                    tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_planes, it * KS, (int)(b * Kpad + blk * TM),
+                                     leader_full);
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        const uint32_t idesc = idesc_i8(TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
-        for (int it = 0; it < n_stages; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            tc_fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_base = smem_u32(smem + s * L::stage_bytes);
-                const uint32_t b_base = a_base + SR * PLANE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < KS / 32; ++ks) {
-                    uint64_t ad[SR], bd[WD];
-#pragma unroll
-                    for (int b = 0; b < SR; ++b)
-                        ad[b] = smem_desc(a_base + b * PLANE_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
-#pragma unroll
-                    for (int a = 0; a < WD; ++a)
-                        bd[a] = smem_desc(b_base + a * PLANE_BYTES + ks * 2 * TN * 16, TN * 16, 128, LAYOUT_NONE);
-                    const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-                    // class c = (weight digit a) + (value digit b), value digit 0 = most significant
-#pragma unroll
-                    for (int a = 0; a < WD; ++a)
-#pragma unroll
-                        for (int b = 0; b < SR; ++b) {
-                            const int c = a + b;
-                            if (c >= NCLASS) continue;
-                            // the first product written to a class overwrites: (a=0,b=c) for c < SR, else (a=c-SR+1,b=SR-1)
-                            const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
-                            if (!(dbg & 1)) umma_i8(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
-                        }
-                }
-                umma_commit(&empty[s]);                      // frees the stage when these MMAs are done
-                if (it == n_stages - 1) umma_commit(accum_full);
+        if (rank != 0) {
+            // -------------------------------------------- relay (peer CTA): one cluster-scope release per
+            // stage tells the leader that this CTA's half of the weight tile is in shared memory
+            // (a cluster-scope release costs a MEMBAR.GPU + L1 invalidate: kept off the generators)
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&bready[s], (it / STAGES) & 1);
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&full[s]), 0));
+                __syncwarp();
             }
-            __syncwarp();
+        }
+        // ------------------------------------------------ MMA issuer (leader CTA)
+        if (rank == 0) {
+            const uint32_t idesc = idesc_i8(2 * TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int chunk = it / chunk_stages;
+                const bool chunk_first = it % chunk_stages == 0;
+                if (chunk_first && chunk > 0) {
+                    mbar_wait_cluster(tmem_empty, (chunk - 1) & 1);     // epilogues of both CTAs drained TMEM
+                    tc_fence_after_sync();
+                }
+                mbar_wait(&bready[s], ph);                    // own generators
+                mbar_wait_cluster(&full[s], ph);              // value planes of both CTAs + the peer's weights
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(smem + s * L::stage_bytes);
+                    const uint32_t b_base = a_base + SR * A_PLANE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < KS / 32; ++ks) {
+                        uint64_t ad[SR], bd[WD];
+#pragma unroll
+                        for (int b = 0; b < SR; ++b)
+                            ad[b] = smem_desc(a_base + b * A_PLANE_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+                        for (int a = 0; a < WD; ++a)
+                            bd[a] = smem_desc(b_base + a * B_PLANE_BYTES + ks * 2 * TNH * 16, TNH * 16, 128,
+                                              LAYOUT_NONE);
+                        const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
+                        // class c = (weight digit a) + (value digit b), value digit 0 = most significant
+#pragma unroll
+                        for (int a = 0; a < WD; ++a)
+#pragma unroll
+                            for (int b = 0; b < SR; ++b) {
+                                const int c = a + b;
+                                if (c >= NCLASS) continue;
+                                // first product written to a class: (0, c) for c < SR, else (c-SR+1, SR-1)
+                                const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
+                                if (!(dbg & 1))
+                                    umma_i8_pair(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
+                            }
+                    }
+                    umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
+                    if (it % chunk_stages == chunk_stages - 1 || it == n_stages - 1) umma_commit_pair(accum_full);
+                }
+                __syncwarp();
+            }
         }
     } else {
-        // ------------------------------------------------ weight generators (B operand)
-        // generator warps 2w, 2w+1 own the 16-byte K chunk w of every stage (16 cells j):
-        // one the cells 0-63 of the tile, the other 64-127; lane l produces the weights of
-        // two cells, so the (x_j, y_j, -|p_j|^2) record of a j is fetched once per two weights.
-        const int chunk = (warp - 2) >> 1;
-        const int cell0 = ((warp - 2) & 1) * 64 + lane;
+        // ------------------------------------------------ weight generators (B operand, 64 cells of the tile)
+        // generator warps 2w, 2w+1 own the 16-byte K chunk w of every stage (16 cells j): one the
+        // cells 0-31, the other the cells 32-63 of this CTA's half tile; one cell per lane.
+        const int kchunk = (warp - 2) >> 1;
+        const int cell = ((warp - 2) & 1) * 32 + lane;         // row of the B planes
+        const long gi = i0 + rank * TNH + cell;                 // global cell index
         const double *my_tab = tab + (lane & (TAB_COPIES - 1));
-        CellI me[CELLS_PER_LANE];
-#pragma unroll
-        for (int cc = 0; cc < CELLS_PER_LANE; ++cc) me[cc] = ci[i0 + cell0 + 32 * cc];
+        const CellI me = ci[gi];
         // the 16 column records of this warp's chunk go through a private 512-byte slot of
         // shared memory (broadcast reads); the next stage's records are prefetched into
         // registers by lanes 0-15 while this stage is computed (L2 latency hidden)
         CellJ *jslot = reinterpret_cast<CellJ *>(smem + L::jrec_off) + (warp - 2) * 16;
-        const CellJ *jsrc = cj + chunk * 16 + (lane & 15);
+        const CellJ *jsrc = cj + kchunk * 16 + (lane & 15);
         uint4 pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc));
         uint4 pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc) + 1);
+        const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31
+        const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const int row = quad * 32 + lane;
+        const long sig = blk * SIGS_PER_TILE + row;
+        const bool row_live = row < SIGS_PER_TILE && sig < K;
+
         for (int it = 0; it < n_stages; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            const long jbase = (long)it * KS + chunk * 16;
+            const long jbase = (long)it * KS + kchunk * 16;
             __syncwarp();
             if (lane < 16) {
                 reinterpret_cast<uint4 *>(jslot + lane)[0] = pre0;
@@ -382,128 +423,126 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                 pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS));
                 pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS) + 1);
             }
-            uint32_t w[CELLS_PER_LANE][16];
-            if (dbg & 2) {
+            // two halves of 8 cells j: the byte planes are packed as soon as 8 weights exist,
+            // which keeps the live register set small (576 threads leave 96 registers each)
+            uint32_t pk[WD][4];
 #pragma unroll
-                for (int cc = 0; cc < CELLS_PER_LANE; ++cc)
+            for (int h = 0; h < 2; ++h) {
+                uint32_t w[8];
+                if (dbg & 2) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) w[cc][e] = 0x01020304u * (e + cc + it);
-            } else
+                    for (int e = 0; e < 8; ++e) w[e] = 0x01020304u * (e + it);
+                } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const double2 xy = *reinterpret_cast<const double2 *>(jslot + e);
-                const double nb = jslot[e].nb;
-#pragma unroll
-                for (int cc = 0; cc < CELLS_PER_LANE; ++cc) {
-                    double t = fma(me[cc].c, nb, me[cc].alpha);
-                    t = fma(me[cc].x2c, xy.x, t);
-                    t = fma(me[cc].y2c, xy.y, t);
-                    w[cc][e] = weight_fixed32(t, my_tab);
+                    for (int e = 0; e < 8; ++e) {
+                        const double2 xy = *reinterpret_cast<const double2 *>(jslot + h * 8 + e);
+                        const double nb = jslot[h * 8 + e].nb;
+                        double t = fma(me.c, nb, me.alpha);
+                        t = fma(me.x2c, xy.x, t);
+                        t = fma(me.y2c, xy.y, t);
+                        w[e] = weight_fixed32(t, my_tab);
+                    }
                 }
-            }
-            // weights[diag] = 0 (Signatures.py:399): at most one chunk of one stage per cell
-            if (jbase < i0 + TN && jbase + 16 > i0) {
+                // weights[diag] = 0 (Signatures.py:399): at most one chunk of one stage per cell
+                if (jbase + h * 8 <= gi && gi < jbase + h * 8 + 8) {
 #pragma unroll
-                for (int cc = 0; cc < CELLS_PER_LANE; ++cc)
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (jbase + e == i0 + cell0 + 32 * cc) w[cc][e] = 0u;
-            }
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t *bst = smem + s * L::stage_bytes + SR * PLANE_BYTES;
-#pragma unroll
-            for (int cc = 0; cc < CELLS_PER_LANE; ++cc) {
-                const int cell = cell0 + 32 * cc;
+                    for (int e = 0; e < 8; ++e)
+                        if (jbase + h * 8 + e == gi) w[e] = 0u;
+                }
 #pragma unroll
                 for (int a = 0; a < WD; ++a) {
                     const uint32_t sel = (3 - a) * 0x11 + 0x40;   // byte (3-a) of x, byte (3-a) of y
-                    uint4 v;
-                    v.x = __byte_perm(__byte_perm(w[cc][0], w[cc][1], sel), __byte_perm(w[cc][2], w[cc][3], sel), 0x5410);
-                    v.y = __byte_perm(__byte_perm(w[cc][4], w[cc][5], sel), __byte_perm(w[cc][6], w[cc][7], sel), 0x5410);
-                    v.z = __byte_perm(__byte_perm(w[cc][8], w[cc][9], sel), __byte_perm(w[cc][10], w[cc][11], sel), 0x5410);
-                    v.w = __byte_perm(__byte_perm(w[cc][12], w[cc][13], sel), __byte_perm(w[cc][14], w[cc][15], sel), 0x5410);
-                    *reinterpret_cast<uint4 *>(bst + a * PLANE_BYTES + (chunk * TN + cell) * 16) = v;
+                    pk[a][2 * h] = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+                    pk[a][2 * h + 1] = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
                 }
             }
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t *bst = smem + s * L::stage_bytes + SR * A_PLANE_BYTES;
+#pragma unroll
+            for (int a = 0; a < WD; ++a)
+                *reinterpret_cast<uint4 *>(bst + a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16) =
+                    make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-        }
+            if (lane == 0) mbar_arrive(&bready[s]);
 
-        // ------------------------------------------------ epilogue
-        mbar_wait(accum_full, 0);
-        tc_fence_after_sync();
-        const int quad = warp & 3;                           // TMEM lanes 32*quad .. +31
-        const int part = (warp - 2) >> 2;                    // columns COLS_PER_WARP*part .. (4 warps per quadrant)
-        constexpr int COLS_PER_WARP = TN / (GEN_WARPS / 4);
-        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        const bool invalid = *flag != 0;
-        // phase A: the ones row (tile row 127) gives sum_j W_ij * 256
-        if (quad == 3) {
+            // -------------------------------------------- drain at the end of a j chunk / epilogue
+            const bool chunk_last = it % chunk_stages == chunk_stages - 1;
+            const bool last = it == n_stages - 1;
+            if (!(chunk_last || last)) continue;
+            const int chunk = it / chunk_stages;
+            mbar_wait(accum_full, chunk & 1);
+            tc_fence_after_sync();
+            // phase A: the ones row (tile row 127) accumulates sum_j W_ij of every column
+            if (quad == 3) {
 #pragma unroll 1
-            for (int b = 0; b < COLS_PER_WARP / 16; ++b) {
-                const int col0 = part * COLS_PER_WARP + b * 16;
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = part * 32 + b * 16;
+                    uint32_t acc[NCLASS][16];
+#pragma unroll
+                    for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                    tmem_ld_wait();
+                    if (lane == 31) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            long long d = 0;
+#pragma unroll
+                            for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                            den_s[col0 + e] += (double)d;
+                        }
+                    }
+                }
+            }
+            named_barrier_sync(1, GEN_THREADS);
+            const Digits dg = decode_range<SR>(range);
+            // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
+            const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
+            const bool invalid = *flag != 0;
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                const int col0 = part * 32 + b * 16;
                 uint32_t acc[NCLASS][16];
 #pragma unroll
                 for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
                 tmem_ld_wait();
-                if (lane == 31) {
+                if (row_live) {
+                    const long ibase = i0 + col0;
+                    double *orow = out + sig * ld_out + ibase;
+                    const double *vrow = values + sig * ld + ibase;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        long long d = 0;
+                        if (ibase + e >= N) continue;
+                        long long num = 0;
 #pragma unroll
-                        for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - c));
-                        den_s[col0 + e] = (double)d * (1.0 / 256.0);
-                    }
-                }
-            }
-        }
-        named_barrier_sync(1, GEN_THREADS);
-        const int row = quad * 32 + lane;
-        const long sig = blk * SIGS_PER_TILE + row;
-        const bool row_live = row < SIGS_PER_TILE && sig < K;
-        const Digits dg = decode_range<SR>(range);
-        const double centre = dg.centre2, inv_scale = 1.0 / dg.scale;
-#pragma unroll 1
-        for (int b = 0; b < COLS_PER_WARP / 16; ++b) {
-            const int col0 = part * COLS_PER_WARP + b * 16;
-            uint32_t acc[NCLASS][16];
-#pragma unroll
-            for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
-            tmem_ld_wait();
-            if (row_live) {
-                double res[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    long long num = 0;
-#pragma unroll
-                    for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - c));
-                    const double den = den_s[col0 + e];
-                    // num = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
-                    // zero row sum -> prediction 0 (:400-402)
-                    res[e] = den > 0.0 ? 0.5 * (((double)num / den) * inv_scale + centre) : 0.0;
-                }
-                const long ibase = i0 + col0;
-                double *orow = out + sig * ld_out + ibase;
-                const double *vrow = values + sig * ld + ibase;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    if (ibase + e < N) {
-                        double r = res[e];
+                        for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                        // partial sums of earlier j chunks are parked in the output row
+                        double total = (double)num;
+                        if (chunk > 0) total += orow[e];
+                        if (!last) {
+                            orow[e] = total;
+                            continue;
+                        }
+                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
+                        // zero row sum -> prediction 0 (Signatures.py:400-402)
+                        const double den = den_s[col0 + e];
+                        double r = den > 0.0 ? 0.5 * ((total / den) * inv_scale + centre) : 0.0;
                         if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
                         if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
                         orow[e] = r;
                     }
                 }
             }
+            if (!last) {
+                // TMEM may be overwritten by the next chunk once every epilogue warp of the pair is done
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
+            }
         }
     }
     tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-        __syncwarp();
-        tmem_dealloc(tmem, 512);
-    }
+    cluster_sync();                                           // no CTA of the pair leaves while the other may signal it
+    if (warp == 0) tmem_dealloc_pair(tmem, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -532,9 +571,10 @@ struct Plan {
 };
 
 bool make_plan(long N, long K, Plan *p) {
-    if (N > 32640) return false;                 // two value digits; three digits + j chunking: not built yet
-    p->sr = 2;
+    if (N > 4000000) return false;               // three balanced digits hold |r * scale| <= 8 355 711
+    p->sr = N <= 32640 ? 2 : 3;
     p->nblk = (K + SIGS_PER_TILE - 1) / SIGS_PER_TILE;
+    p->nblk = (p->nblk + 1) / 2 * 2;             // CTA pairs own two blocks
     p->Kpad = p->nblk * TM;
     p->Npad = (long)align_up((size_t)N, KS);
     size_t off = 0;
@@ -564,7 +604,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
                       int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Plan p;
     if (!make_plan(N, K, &p)) {
-        fp::set_error("fp_consistency: FP_PRECISION_TC supports N <= 32640 cells in this build (N=%ld)", (long)N);
+        fp::set_error("fp_consistency: FP_PRECISION_TC supports N <= 4000000 cells (N=%ld)", (long)N);
         return FP_EUNSUPPORTED;
     }
     if (!workspace || workspace_bytes < p.total) {
@@ -602,7 +642,10 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
     FP_CHECK_LAUNCH("cell_setup_kernel");
     {
         dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
-        pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
+        if (p.sr == 2)
+            pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
+        else
+            pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
         FP_CHECK_LAUNCH("pack_values_kernel");
     }
     CUtensorMap tmap;
@@ -619,16 +662,25 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
             return FP_ECUDA;
         }
     }
-    using L = SmemLayout<2>;
     static bool attr_set = false;
     if (!attr_set) {
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           L::total));
+                                           SmemLayout<2>::total));
+        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           SmemLayout<3>::total));
         attr_set = true;
     }
-    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)p.nblk);
-    consistency_tc_kernel<2><<<grid, THREADS, L::total, st>>>(tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad,
-                                                              (int)(p.Npad / KS), output_kind, range, flag, getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0);
+    const int n_stages = (int)(p.Npad / KS);
+    const int dbg = getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0;
+    // x: pair index (cell tile) * 2 + CTA rank in the pair; y: pair of signature blocks
+    dim3 grid((unsigned)(2 * ((N + TN - 1) / TN)), (unsigned)(p.nblk / 2));
+    if (p.sr == 2)
+        consistency_tc_kernel<2><<<grid, THREADS, SmemLayout<2>::total, st>>>(
+            tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, n_stages, output_kind, range, flag, dbg);
+    else
+        consistency_tc_kernel<3><<<grid, THREADS, SmemLayout<3>::total, st>>>(
+            tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, CHUNK_STAGES_3, output_kind, range, flag,
+            dbg);
     FP_CHECK_LAUNCH("consistency_tc_kernel");
     return FP_OK;
 }

@@ -54,4 +54,6 @@ worst = max(worst, case(4097, 130, 3, outliers=2, dup=3))
 worst = max(worst, case(2000, 40, 4, per_cell=True))
 worst = max(worst, case(2000, 300, 5, kind=_native.OUT_PREDICTION, binary=True))
 worst = max(worst, case(20000, 260, 6, outliers=1))
+worst = max(worst, case(33000, 130, 7, outliers=1))
+worst = max(worst, case(40000, 20, 8))
 print("WORST rel", worst)
