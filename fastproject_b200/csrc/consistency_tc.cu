@@ -71,7 +71,7 @@ struct SmemLayout {
     static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
     static constexpr int table_off = stages * stage_bytes;
     static constexpr int jrec_off = table_off + TAB * TAB_COPIES * 8;       // per generator warp: 16 CellJ
-    static constexpr int den_off = jrec_off + GEN_WARPS * 16 * 32;
+    static constexpr int den_off = jrec_off + 2 * GEN_WARPS * 16 * 32;      // double buffered
     static constexpr int bar_off = den_off + TN * 8;
     static constexpr int total = bar_off + 256;   // 18 mbarriers + the TMEM slot
 };
@@ -395,13 +395,18 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         const long gi = i0 + rank * TNH + cell;                 // global cell index
         const double *my_tab = tab + (lane & (TAB_COPIES - 1));
         const CellI me = ci[gi];
-        // the 16 column records of this warp's chunk go through a private 512-byte slot of
-        // shared memory (broadcast reads); the next stage's records are prefetched into
-        // registers by lanes 0-15 while this stage is computed (L2 latency hidden)
-        CellJ *jslot = reinterpret_cast<CellJ *>(smem + L::jrec_off) + (warp - 2) * 16;
-        const CellJ *jsrc = cj + kchunk * 16 + (lane & 15);
-        uint4 pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc));
-        uint4 pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc) + 1);
+        // the 16 column records of this warp's chunk go through a private, double-buffered
+        // 512-byte slot of shared memory (broadcast reads); cp.async brings the next stage's
+        // records in while this stage is computed -- no registers held across the L2 latency
+        CellJ *jslot = reinterpret_cast<CellJ *>(smem + L::jrec_off) + (warp - 2) * 32;
+        const char *jsrc = reinterpret_cast<const char *>(cj + kchunk * 16) + lane * 16;
+        auto prefetch_records = [&](int it_next) {
+            const uint32_t dst = smem_u32(reinterpret_cast<char *>(jslot + (it_next & 1) * 16) + lane * 16);
+            const char *src = jsrc + (long)it_next * KS * sizeof(CellJ);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        prefetch_records(0);
         const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31
         const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
@@ -413,16 +418,10 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             const long jbase = (long)it * KS + kchunk * 16;
-            __syncwarp();
-            if (lane < 16) {
-                reinterpret_cast<uint4 *>(jslot + lane)[0] = pre0;
-                reinterpret_cast<uint4 *>(jslot + lane)[1] = pre1;
-            }
-            __syncwarp();
-            if (it + 1 < n_stages) {
-                pre0 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS));
-                pre1 = __ldg(reinterpret_cast<const uint4 *>(jsrc + (long)(it + 1) * KS) + 1);
-            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                                      // records of stage it visible; slot of it+1 free
+            if (it + 1 < n_stages) prefetch_records(it + 1);
+            const CellJ *jr = jslot + (it & 1) * 16;
             // two halves of 8 cells j: the byte planes are packed as soon as 8 weights exist,
             // which keeps the live register set small (576 threads leave 96 registers each)
             uint32_t pk[WD][4];
@@ -435,8 +434,8 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                 } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const double2 xy = *reinterpret_cast<const double2 *>(jslot + h * 8 + e);
-                        const double nb = jslot[h * 8 + e].nb;
+                        const double2 xy = *reinterpret_cast<const double2 *>(jr + h * 8 + e);
+                        const double nb = jr[h * 8 + e].nb;
                         double t = fma(me.c, nb, me.alpha);
                         t = fma(me.x2c, xy.x, t);
                         t = fma(me.y2c, xy.y, t);
