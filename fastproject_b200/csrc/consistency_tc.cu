@@ -414,7 +414,12 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         const long sig = blk * SIGS_PER_TILE + row;
         const bool row_live = row < SIGS_PER_TILE && sig < K;
 
-        for (int it = 0; it < n_stages; ++it) {
+        const int n_chunks = (n_stages + chunk_stages - 1) / chunk_stages;
+#pragma unroll 1
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+          const int it_end = min(n_stages, (chunk + 1) * chunk_stages);
+#pragma unroll 1
+          for (int it = chunk * chunk_stages; it < it_end; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             const long jbase = (long)it * KS + kchunk * 16;
@@ -464,12 +469,10 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bready[s]);
+          }
 
             // -------------------------------------------- drain at the end of a j chunk / epilogue
-            const bool chunk_last = it % chunk_stages == chunk_stages - 1;
-            const bool last = it == n_stages - 1;
-            if (!(chunk_last || last)) continue;
-            const int chunk = it / chunk_stages;
+            const bool last = it_end == n_stages;
             mbar_wait(accum_full, chunk & 1);
             tc_fence_after_sync();
             // phase A: the ones row (tile row 127) accumulates sum_j W_ij of every column
