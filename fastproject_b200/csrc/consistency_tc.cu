@@ -61,9 +61,6 @@ constexpr int TAB = 128;           // 2^(k/128) table ...
 constexpr int TAB_COPIES = 16;     // ... one copy per lane of a half-warp: LDS.64 without bank conflicts
 // s32 accumulators: a class sums at most 3 digit products of magnitude <= 255 * 128 per j
 constexpr int CHUNK_STAGES_3 = 128;       // three value digits: drain every 16 384 cells j
-// padding / dead rows use a large finite exponent instead of -inf so that the
-// integer part of t always fits the 32-bit extraction in weight_fixed32
-constexpr double T_DEAD = -1.0e6;
 
 template <int SR>
 struct SmemLayout {
@@ -117,13 +114,15 @@ cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ 
     // other cell) has row sum 0 -> prediction 0 (Signatures.py:400-402)
     const bool dead = !live || !(m < __longlong_as_double(0x7ff0000000000000LL)) || exp(-m / s2) == 0.0;
     // - 2^-30: keeps t_ij <= 0 against the rounding of the expanded form (a common row
-    // factor 2^(-2^-30), cancels in the quotient)
-    a.alpha = dead ? T_DEAD : c * (m - fma(xi, xi, yi * yi)) - 9.313225746154785e-10;
+    // factor 2^(-2^-30), cancels in the quotient).  A dead row gets a large negative exponent
+    // (all its weights round to 0 -> row sum 0 -> prediction 0).
+    a.alpha = dead ? -1.0e5 : c * (m - fma(xi, xi, yi * yi)) - 9.313225746154785e-10;
     ci[i] = a;
     CellJ b;
     b.x = xi;
     b.y = yi;
-    b.nb = live ? -fma(xi, xi, yi * yi) : T_DEAD;            // c * nb <= -1e6 * log2(e) / sigma^2
+    // padded columns need no special weight: their value digits (ones row included) are zero
+    b.nb = -fma(xi, xi, yi * yi);
     b.pad = 0.0;
     cj[i] = b;
 }
@@ -245,21 +244,21 @@ pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, l
 // (remainder < 2^-40), exponent n added to the exponent field, + 2^52 rounds to
 // an integer.  tab points at this lane's copy of the table (stride TAB_COPIES).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t weight_fixed32(double t, const double *__restrict__ tab) {
+__device__ __forceinline__ uint32_t weight_fixed32(double t, const char *__restrict__ tab_lane) {
     constexpr double MAGIC = 52776558133248.0;              // 1.5 * 2^45: ulp = 2^-7
     constexpr double L1 = 0.69314718055994530942, L2 = 0.24022650695910071233, L3 = 0.05550410866482157995;
-    // t > -40 <=> high word below that of -40.0 (sign bit set, larger magnitude = larger word)
-    const bool ok = (uint32_t)__double2hiint(t) < 0xC0440000u;
     const double z = t + MAGIC;
     const int ti = __double2loint(z);                       // round(128 t), two's complement
     const double g = t - (z - MAGIC);                       // |g| <= 2^-8
     const double p = g * fma(g, fma(g, L3, L2), L1);        // 2^g - 1
-    const double T = tab[(ti & (TAB - 1)) * TAB_COPIES];    // 2^(k/128) * (2^32 - 1)
+    // 2^(k/128) * (2^32 - 1), k = ti mod 128; the lane's copy of entry k is 128 bytes after entry k-1
+    const double T = *reinterpret_cast<const double *>(tab_lane + ((ti & (TAB - 1)) << 7));
     const double v = fma(T, p, T);
-    const int q = ti >> 7;                                  // floor(t) <= 0
+    // floor(t) <= 0 goes into the exponent field; below 2^-64 the weight rounds to 0 anyway, and the
+    // clamp keeps the exponent arithmetic in range for any t > -2^24 (cells 1000 bandwidths apart)
+    const int q = max(ti >> 7, -64);
     const double vs = __hiloint2double(__double2hiint(v) + (q << 20), __double2loint(v));
-    const uint32_t w = (uint32_t)__double2loint(vs + 4503599627370496.0);   // + 2^52: round to integer
-    return ok ? w : 0u;
+    return (uint32_t)__double2loint(vs + 4503599627370496.0);   // + 2^52: round to integer
 }
 
 template <int SR>
@@ -393,7 +392,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         const int kchunk = (warp - 2) >> 1;
         const int cell = ((warp - 2) & 1) * 32 + lane;         // row of the B planes
         const long gi = i0 + rank * TNH + cell;                 // global cell index
-        const double *my_tab = tab + (lane & (TAB_COPIES - 1));
+        const char *my_tab = reinterpret_cast<const char *>(tab + (lane & (TAB_COPIES - 1)));
         const CellI me = ci[gi];
         // the 16 column records of this warp's chunk go through a private, double-buffered
         // 512-byte slot of shared memory (broadcast reads); cp.async brings the next stage's
@@ -447,12 +446,6 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                         w[e] = weight_fixed32(t, my_tab);
                     }
                 }
-                // weights[diag] = 0 (Signatures.py:399): at most one chunk of one stage per cell
-                if (jbase + h * 8 <= gi && gi < jbase + h * 8 + 8) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (jbase + h * 8 + e == gi) w[e] = 0u;
-                }
 #pragma unroll
                 for (int a = 0; a < WD; ++a) {
                     const uint32_t sel = (3 - a) * 0x11 + 0x40;   // byte (3-a) of x, byte (3-a) of y
@@ -466,6 +459,13 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             for (int a = 0; a < WD; ++a)
                 *reinterpret_cast<uint4 *>(bst + a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16) =
                     make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
+            // weights[diag] = 0 (Signatures.py:399): the cell's own column lies in one chunk of one
+            // stage; its four digit bytes are cleared after the store instead of testing every weight
+            const long dj = gi - jbase;
+            if (dj >= 0 && dj < 16) {
+#pragma unroll
+                for (int a = 0; a < WD; ++a) bst[a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16 + dj] = 0;
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bready[s]);
