@@ -184,6 +184,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at VERSION/INFO level; stdout carries the JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("FP_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=device)
     if rank == 0:
         ge.build()
@@ -306,10 +308,10 @@ def run_b200(args):
     result["checksum_p"] = float(out[0].sum())
     result["checksum_median"] = float(out[1].sum())
 
-    if rank == 0 and world == 1 and not args.no_e2e:
-        result["e2e"] = run_e2e(args, cfg, wl, precision)
-    elif world > 1:
-        result["e2e"] = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, cfg, wl, precision, world, device)
+        if rank == 0:
+            result["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cfg, wl, budget_s=25.0)
     if world > 1:
@@ -319,13 +321,16 @@ def run_b200(args):
         print(json.dumps(result))
 
 
-def run_e2e(args, cfg, wl, precision):
+def run_e2e(args, cfg, wl, precision, world=1, device=None):
     """Public API with HOST buffers: H2D of X and W from pinned memory, CSR
     packing, all kernels, D2H of the real signatures' scores and of the
-    result matrices, every step."""
+    result matrices, every step.  With N ranks every rank runs the same calls on
+    its own block of signatures (``distributed=True``: medians all-gathered inside
+    ``sigs_vs_projections``); the time is the max over ranks."""
     import io
     import contextlib
     import torch
+    import torch.distributed as dist
     from fastproject_b200 import Signatures as S, _engine as E, synth
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
     xh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
@@ -339,14 +344,21 @@ def run_e2e(args, cfg, wl, precision):
     for it in range(steps + 1):
         E.clear_device_cache()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5)
         rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5)
-        res = S.sigs_vs_projections(wl["projections"], real, rnd, SIGMA, precision=precision)
+        res = S.sigs_vs_projections(wl["projections"], real, rnd, SIGMA, precision=precision,
+                                    distributed=world > 1)
         first = next(iter(real.values()))
         host_scores = first._batch.host_scores()                 # D2H of all real scores
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if world > 1:
+            tmax = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax[0])
         if it > 0:
             times.append(dt)
         d2h = host_scores.nbytes + res[2].nbytes + res[3].nbytes + res[4].nbytes
@@ -355,9 +367,10 @@ def run_e2e(args, cfg, wl, precision):
     n_rows = len(real) + len(rnd)
     nnz = sum(len(s.sig_dict) for s in wl["real"]) + sum(len(s.sig_dict) for s in wl["rnd"])
     h2d = 2 * G * N * 8 + nnz * 5 + (n_rows + 1) * 4 + P * 2 * N * 8
-    return {"value": n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "s_per_step": t, "steps": len(times),
-            "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections, pinned host inputs"}
+    return {"value": world * n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * world,
+            "d2h_bytes_per_step": int(d2h) * world, "s_per_step": t, "steps": len(times),
+            "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections(distributed=%s), "
+                   "pinned host inputs, per rank" % (world > 1)}
 
 
 # ----------------------------------------------------------------------------

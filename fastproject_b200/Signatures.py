@@ -194,7 +194,7 @@ def _factor_design(values):
 
 
 def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
-                        NEIGHBORHOOD_SIZE=0.33, precision=None, sigma_per_cell=None):
+                        NEIGHBORHOOD_SIZE=0.33, precision=None, sigma_per_cell=None, distributed=False):
     """Evaluates the significance of each signature vs each projection
     (Signatures.py:300-534).
 
@@ -206,6 +206,11 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
         FASTPROJECT_B200_PRECISION, else "fp64"
     :param sigma_per_cell: (extension) optional (N,) array of per-cell bandwidths
         replacing NEIGHBORHOOD_SIZE
+    :param distributed: (extension) one process per GPU (``torch.distributed`` initialised):
+        every rank passes ITS block of the signature dictionaries; the per-pair medians are
+        all-gathered (the only exchange), the random background pools all ranks, and every
+        rank returns the full result with rows in rank order -- what the reference would
+        return for the concatenated dictionaries
     :return: (sp_row_labels, sp_col_labels, sig_proj_matrix, sig_proj_matrix_p (log10 q),
               random_sig_proj_matrix, random_sig_score_keys)
     """
@@ -234,8 +239,11 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     rnd_objs = [random_sig_scores_dict[k] for k in random_sig_score_keys]
     ranks = _device_rank_rows(std_objs + rnd_objs, N_SAMPLES)           # :359-369
 
-    order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
-                                                [o.numGenes for o in std_objs])
+    if distributed:
+        order = gptr = sig_group = np.zeros((0,), dtype=np.int32)       # grouped globally after the gather
+    else:
+        order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
+                                                    [o.numGenes for o in std_objs])
     d_order = _engine.to_device(order, torch.int32)
     d_gptr = _engine.to_device(gptr, torch.int32)
     d_group = _engine.to_device(sig_group, torch.int32)
@@ -264,7 +272,7 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             _engine.consistency(coords, sig2, ranks, N_SAMPLES, out=dissim, precision=precision)
             med = _engine.row_medians(dissim, N_SAMPLES)                # :409, :414
             med_all[i] = med
-            if N_SIGNATURES:
+            if N_SIGNATURES and not distributed:
                 p, _, _ = _engine.background_pvalues(med[:N_SIGNATURES], d_group,
                                                      med[N_SIGNATURES:], d_order, d_gptr)   # :417-442
                 p_all[i] = p
@@ -279,9 +287,39 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             factor_sig_proj_matrix[j, i] = cons
             factor_sig_proj_matrix_p[j, i] = pval
 
-    med_host = med_all.cpu().numpy()
-    sig_proj_matrix = 1 - med_host[:, :N_SIGNATURES].T / N_SAMPLES      # :444
-    random_sig_proj_matrix = 1 - med_host[:, N_SIGNATURES:].T / N_SAMPLES   # :445
+    if distributed:
+        # the one exchange of the multi-GPU path: medians (and the few host-side rows)
+        from . import distributed as D
+        import torch.distributed as dist
+        world_size, _ = D.world()
+        shape_all = D.all_gather_counts([N_SIGNATURES, N_SIGNATURES + N_RANDOM], device=dev).reshape(world_size, 2)
+        counts = [o.numGenes for o in std_objs] + [o.numGenes for o in rnd_objs]
+        counts_all = D.all_gather_counts(counts, device=dev)
+        bg = D.GlobalBackground(counts_all, [int(v) for v in shape_all[:, 0]],
+                                [int(v) for v in shape_all[:, 1]], dev)
+        gathered = D.all_gather_rows(med_all)
+        p_all = bg.pvalues(gathered) if len(bg.real_cols_host) else torch.empty(
+            (N_PROJECTIONS, 0), dtype=torch.float64, device=dev)
+        med_host = gathered.cpu().numpy()
+        sig_proj_matrix = 1 - med_host[:, bg.real_cols_host].T / N_SAMPLES
+        random_sig_proj_matrix = 1 - med_host[:, bg.rnd_cols_host].T / N_SAMPLES
+        small = [None] * world_size
+        dist.all_gather_object(small, dict(std=sp_row_labels, fac=sp_row_labels_factors,
+                                           pnum=sp_row_labels_pnum, rkeys=random_sig_score_keys,
+                                           fm=factor_sig_proj_matrix, fp=factor_sig_proj_matrix_p,
+                                           pm=pnum_sig_proj_matrix, pp=pnum_sig_proj_matrix_p))
+        sp_row_labels = [n for part in small for n in part["std"]]
+        sp_row_labels_factors = [n for part in small for n in part["fac"]]
+        sp_row_labels_pnum = [n for part in small for n in part["pnum"]]
+        random_sig_score_keys = [n for part in small for n in part["rkeys"]]
+        factor_sig_proj_matrix = np.concatenate([part["fm"] for part in small], axis=0)
+        factor_sig_proj_matrix_p = np.concatenate([part["fp"] for part in small], axis=0)
+        pnum_sig_proj_matrix = np.concatenate([part["pm"] for part in small], axis=0)
+        pnum_sig_proj_matrix_p = np.concatenate([part["pp"] for part in small], axis=0)
+    else:
+        med_host = med_all.cpu().numpy()
+        sig_proj_matrix = 1 - med_host[:, :N_SIGNATURES].T / N_SAMPLES      # :444
+        random_sig_proj_matrix = 1 - med_host[:, N_SIGNATURES:].T / N_SAMPLES   # :445
     sig_proj_matrix_p = p_all.cpu().numpy().T.copy()
 
     sig_proj_matrix = np.concatenate((sig_proj_matrix, factor_sig_proj_matrix,

@@ -13,8 +13,14 @@
 
 namespace {
 
-// v1 mapping: one warp = one signature x 32 consecutive cells; lanes read
-// 256 contiguous bytes of a gene row (two full 128-byte lines) per operand.
+// Mapping: one warp = one signature x 32 consecutive cells; lanes read 256
+// contiguous bytes of a gene row (two full 128-byte lines) per operand.
+// Launch order: blockIdx.x runs over the signature tiles of ONE slab of 128
+// cells, blockIdx.y over the slabs, so the CTAs in flight all gather from the
+// same G x 128-cell slab of X and W (30 MB at G = 15 000): it is read from HBM
+// once and served from L2 to the ~15 signatures that touch each gene row.
+// (Round-1 profile of the transposed order: 73.9 GB of DRAM reads for 4.8 GB of
+// input, L2 hit rate 0.7 %.)
 constexpr int kCellsPerBlock = 128;   // blockDim.x
 constexpr int kSigsPerBlock = 4;      // blockDim.y
 
@@ -32,11 +38,12 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
                     const int32_t *__restrict__ sig_ptr, const int32_t *__restrict__ sig_gene,
                     const int8_t *__restrict__ sig_sign, long K,
                     const double *__restrict__ gene_mu, double *__restrict__ out, long ld_out) {
-    const long cell = (long)blockIdx.x * kCellsPerBlock + threadIdx.x;
+    for (long slab = blockIdx.y; slab * kCellsPerBlock < N; slab += gridDim.y) {
+    const long cell = slab * kCellsPerBlock + threadIdx.x;
     const bool live = cell < N;
     const long c = live ? cell : (N - 1);
-    for (long k = (long)blockIdx.y * kSigsPerBlock + threadIdx.y; k < K;
-         k += (long)gridDim.y * kSigsPerBlock) {
+    for (long k = (long)blockIdx.x * kSigsPerBlock + threadIdx.y; k < K;
+         k += (long)gridDim.x * kSigsPerBlock) {
         const int beg = sig_ptr[k], end = sig_ptr[k + 1];
         double num = 0.0, den = 0.0, aux = 0.0;
         for (int t = beg; t < end; ++t) {
@@ -78,6 +85,7 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
             score = __ddiv_rn(num, den);
         }
         if (live) out[k * ld_out + cell] = score;
+    }
     }
 }
 
@@ -144,10 +152,10 @@ extern "C" int fp_score_signatures(int method, const double *X, const double *W,
     FP_CHECK_ARG(method != FP_METHOD_IMPUTED || gene_mu, "fp_score_signatures: imputed needs gene_mu");
     if (K == 0) return FP_OK;
     dim3 block(kCellsPerBlock, kSigsPerBlock);
-    const long cell_tiles = (N + kCellsPerBlock - 1) / kCellsPerBlock;
-    long sig_tiles = (K + kSigsPerBlock - 1) / kSigsPerBlock;
-    if (sig_tiles > 65535) sig_tiles = 65535;
-    dim3 grid((unsigned)cell_tiles, (unsigned)sig_tiles);
+    long cell_tiles = (N + kCellsPerBlock - 1) / kCellsPerBlock;
+    if (cell_tiles > 65535) cell_tiles = 65535;
+    const long sig_tiles = (K + kSigsPerBlock - 1) / kSigsPerBlock;
+    dim3 grid((unsigned)sig_tiles, (unsigned)cell_tiles);
     cudaStream_t st = fp::as_stream(stream);
 #define FP_LAUNCH_SCORE(M)                                                                    \
     score_gather_kernel<M><<<grid, block, 0, st>>>(X, W, Z, N, ld, sig_ptr, sig_gene, sig_sign, \

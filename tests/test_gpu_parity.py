@@ -331,3 +331,27 @@ def test_smoke_entry_point():
     import __graft_entry__ as ge
     with contextlib.redirect_stdout(io.StringIO()):
         ge.smoke()
+
+
+def test_distributed_mode_single_rank_equals_local(fp):
+    """distributed=True on a one-rank NCCL group takes the all-gather path and must return
+    exactly what the local path returns (the two-rank exchange itself is covered on CPU by
+    tests/test_distributed_cpu.py and on the GPUs by bench.py --gpus N)."""
+    import os
+    import torch.distributed as dist
+    c = G.load("case_synth_even")
+    want = _svp(fp, c, precision="fp64")
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    try:
+        got = _svp(fp, c, precision="fp64", distributed=True)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert got[0] == want[0] and got[1] == want[1] and got[5] == want[5]
+    for a, b in zip(got[2:5], want[2:5]):
+        assert np.array_equal(a, b)
