@@ -269,7 +269,9 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             raise ValueError("projection %r has shape %s, expected (2, %d)"
                              % (proj, tuple(coords.shape), N_SAMPLES))
         if ranks.shape[0]:
-            _engine.consistency(coords, sig2, ranks, N_SAMPLES, out=dissim, precision=precision)
+            # the rank matrix is the same for every projection: its digit planes are packed once
+            _engine.consistency(coords, sig2, ranks, N_SAMPLES, out=dissim, precision=precision,
+                                reuse_packed=i > 0, slot="svp")
             med = _engine.row_medians(dissim, N_SAMPLES)                # :409, :414
             med_all[i] = med
             if N_SIGNATURES and not distributed:

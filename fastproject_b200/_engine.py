@@ -165,8 +165,10 @@ def rank_rows(scores, n):
 
 
 def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_ABS_ERROR,
-                precision=None):
-    """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor."""
+                precision=None, reuse_packed=False, slot="default"):
+    """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor.
+    ``reuse_packed``: the previous call on the same workspace ``slot`` had the same
+    ``ranks`` (another projection): the tensor-core path skips re-packing them."""
     k, ld = ranks.shape
     if out is None:
         out = torch.empty((k, ld), dtype=torch.float64, device=ranks.device)
@@ -174,7 +176,9 @@ def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_AB
     vec = sigma_sq if isinstance(sigma_sq, torch.Tensor) else None
     scalar = 0.0 if vec is not None else float(sigma_sq)
     nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
-    ws, ws_ptr = _workspace(nbytes, ranks.device)
+    ws, ws_ptr = _workspace(nbytes, ranks.device, slot)
+    if reuse_packed and mode == _native.PRECISION_CODES["tc"]:
+        output_kind |= _native.REUSE_PACKED
     _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
                  ptr(out), out.stride(0), output_kind, mode, ws_ptr, nbytes, stream_ptr())
     return out
@@ -184,13 +188,13 @@ _WS_ALIGN = 1024
 _ws_cache = dict()
 
 
-def _workspace(nbytes, device):
+def _workspace(nbytes, device, slot="default"):
     """Scratch buffer for one call (1024-byte aligned: the TMA / UMMA tiles of
     the tensor-core path need it).  The largest buffer per device is kept and
     reused; all work of a process goes to one stream at a time."""
     if not nbytes:
         return None, 0
-    key = str(device)
+    key = (str(device), slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes + _WS_ALIGN:
         buf = torch.empty((nbytes + _WS_ALIGN,), dtype=torch.uint8, device=device)

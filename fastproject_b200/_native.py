@@ -40,6 +40,7 @@ SIGNATURES = {
 METHOD_CODES = {"naive": 0, "weighted_avg": 1, "imputed": 2, "only_nonzero": 3}
 PRECISION_CODES = {"fp64": 0, "tc": 1}
 OUT_ABS_ERROR, OUT_PREDICTION = 0, 1
+REUSE_PACKED = 0x100
 
 _lib = None
 

@@ -81,21 +81,29 @@ struct __align__(32) CellJ { double x, y, nb, pad; };         // column side
 // per-cell set-up: nearest-neighbour distance (row scale) and the coefficients
 // of t_ij = log2(e)/sigma_i^2 * (m_i - d_ij^2) = alpha_i + c_i*nb_j + X_i*x_j + Y_i*y_j
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dist_key(double v) {   // v >= 0: bit pattern is monotone
+    return (unsigned long long)__double_as_longlong(v);
+}
+
+// nearest-neighbour squared distance of every cell; the j range is split over blockIdx.y and
+// combined with atomicMin (non-negative doubles order like their bit patterns)
 __global__ void __launch_bounds__(256)
-cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ sigma_sq,
-                  double sigma_sq_scalar, long N, long Npad, CellI *__restrict__ ci, CellJ *__restrict__ cj) {
+nearest_neighbour_kernel(const double *__restrict__ coords, long N, unsigned long long *__restrict__ nn) {
     __shared__ double sx[256], sy[256];
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
     const double *cx = coords, *cy = coords + N;
     const bool live = i < N;
     const double xi = live ? cx[i] : 0.0, yi = live ? cy[i] : 0.0;
     double m = __longlong_as_double(0x7ff0000000000000LL);   // +inf
-    for (long j0 = 0; j0 < N; j0 += 256) {
+    const long jper = ((N + gridDim.y - 1) / gridDim.y + 255) / 256 * 256;
+    const long jlo = (long)blockIdx.y * jper, jhi = min(N, jlo + jper);
+    for (long j0 = jlo; j0 < jhi; j0 += 256) {
         const long jj = j0 + threadIdx.x;
         sx[threadIdx.x] = jj < N ? cx[jj] : 0.0;
         sy[threadIdx.x] = jj < N ? cy[jj] : 0.0;
         __syncthreads();
-        const int lim = (int)((N - j0) < 256 ? (N - j0) : 256);
+        const int lim = (int)((jhi - j0) < 256 ? (jhi - j0) : 256);
+#pragma unroll 4
         for (int t = 0; t < lim; ++t) {
             const double dx = xi - sx[t], dy = yi - sy[t];
             const double d2 = fma(dx, dx, dy * dy);
@@ -103,7 +111,19 @@ cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ 
         }
         __syncthreads();
     }
+    if (live) atomicMin(&nn[i], dist_key(m));
+}
+
+__global__ void __launch_bounds__(256)
+cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ sigma_sq,
+                  double sigma_sq_scalar, long N, long Npad, const unsigned long long *__restrict__ nn,
+                  CellI *__restrict__ ci, CellJ *__restrict__ cj) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
     if (i >= Npad) return;
+    const double *cx = coords, *cy = coords + N;
+    const bool live = i < N;
+    const double xi = live ? cx[i] : 0.0, yi = live ? cy[i] : 0.0;
+    const double m = live ? __longlong_as_double((long long)nn[i]) : __longlong_as_double(0x7ff0000000000000LL);
     const double s2 = sigma_sq ? (live ? sigma_sq[i] : 1.0) : sigma_sq_scalar;
     const double c = 1.4426950408889634074 / s2;             // log2(e) / sigma^2
     CellI a;
@@ -569,7 +589,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Plan {
     int sr;
     long nblk, Kpad, Npad;
-    size_t planes_off, ci_off, cj_off, flag_off, range_off, total;
+    size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, total;
 };
 
 bool make_plan(long N, long K, Plan *p) {
@@ -586,6 +606,8 @@ bool make_plan(long N, long K, Plan *p) {
     off += align_up((size_t)p->Npad * sizeof(CellI), 1024);
     p->cj_off = off;
     off += align_up((size_t)p->Npad * sizeof(CellJ), 1024);
+    p->nn_off = off;
+    off += align_up((size_t)p->Npad * 8, 1024);
     p->flag_off = off;
     p->range_off = off + 64;
     off += 1024;
@@ -629,26 +651,37 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
     int *flag = reinterpret_cast<int *>(ws + p.flag_off);
 
     unsigned long long *range = reinterpret_cast<unsigned long long *>(ws + p.range_off);
-    FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
-    FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
-    FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
-    {
+    unsigned long long *nn = reinterpret_cast<unsigned long long *>(ws + p.nn_off);
+    const bool reuse_packed = (output_kind & FP_REUSE_PACKED) != 0;
+    output_kind &= ~FP_REUSE_PACKED;
+    if (!reuse_packed) {
+        // value range and digit planes depend on the values only, not on the projection
+        FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
+        FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
+        FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
         unsigned gy = (unsigned)(K < 296 ? K : 296);
         unsigned gx = (unsigned)((N + 2047) / 2048);
         if (gx > 4) gx = 4;
         value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
         FP_CHECK_LAUNCH("value_range_kernel");
-    }
-    cell_setup_kernel<<<(unsigned)(p.Npad / 256 + 1), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N, p.Npad,
-                                                                   ci, cj);
-    FP_CHECK_LAUNCH("cell_setup_kernel");
-    {
         dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
         if (p.sr == 2)
             pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
         else
             pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
         FP_CHECK_LAUNCH("pack_values_kernel");
+    }
+    {
+        FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // > +inf as a key
+        const unsigned bx = (unsigned)((N + 255) / 256);
+        unsigned by = (unsigned)((4 * fp::sm_count() + bx - 1) / bx);
+        if (by < 1) by = 1;
+        if ((long)by * 256 > N) by = (unsigned)((N + 255) / 256);
+        nearest_neighbour_kernel<<<dim3(bx, by), 256, 0, st>>>(coords, N, nn);
+        FP_CHECK_LAUNCH("nearest_neighbour_kernel");
+        cell_setup_kernel<<<(unsigned)((p.Npad + 255) / 256), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N,
+                                                                            p.Npad, nn, ci, cj);
+        FP_CHECK_LAUNCH("cell_setup_kernel");
     }
     CUtensorMap tmap;
     {

@@ -63,6 +63,10 @@ extern "C" {
 /* what fp_consistency writes */
 #define FP_OUT_ABS_ERROR       0   /* |r - prediction|  (Signatures.py:408, 413, 462, 470) */
 #define FP_OUT_PREDICTION      1   /* the prediction itself (factor branch, :493, 505)     */
+/* OR-ed into output_kind (FP_PRECISION_TC only): the workspace still holds the packed
+ * digit planes of the previous call with the SAME values / N / K (the reference loops
+ * over projections with one rank matrix, Signatures.py:393), so packing is skipped */
+#define FP_REUSE_PACKED      0x100
 
 /* arithmetic of the neighbourhood contraction in fp_consistency */
 #define FP_PRECISION_FP64      0   /* float64 FMA on the FP64 pipe (verifier)           */
