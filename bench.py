@@ -277,9 +277,13 @@ def run_b200(args):
     peaks = measured_peaks()
     cons_flops = 2.0 * N * N * (n_rows + 1)                   # per launch (one projection)
     score_bytes = G * N * 16.0 + N * n_rows * 8.0 + 5.0 * nnz  # per launch
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of
+    # this exact configuration (profiles/r01_summary_tc.md); None where no capture exists
+    ncu_traffic = {("C2", "tc", 1): 726867712 + 552165376, ("C2", "fp64", 1): 603465984 + 551192064}
     roofline = dict(bound="tensor", kernel="fp_consistency[%s]" % precision,
                     achieved=cons_flops / (cons_ms * 1e-3) / 1e12, peak=peaks["tflops"],
-                    unit="TFLOP/s", traffic=None, peak_source=peaks["source"],
+                    unit="TFLOP/s", traffic=ncu_traffic.get((args.workload, precision, 1)),
+                    peak_source=peaks["source"],
                     launch_ms=cons_ms, share_of_step=cons_ms * P / ms_step)
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
     roofline_score = dict(bound="hbm", kernel="fp_score_signatures", unit="GB/s",
