@@ -49,6 +49,16 @@ SIZES = [5, 10, 20, 50, 100, 200]
 SIGMA = 0.33
 
 
+def describe_config(workload, cfg, n_real, n_rnd, precision, world):
+    """The ``config`` object of the JSON line -- identical for both arms."""
+    G, N, P = cfg["G"], cfg["N"], cfg["P"]
+    return {"workload": "%s: %d cells x %d genes, %d real + %d random signatures per GPU, "
+                        "%d projections, sigma=0.33" % (workload, N, G, n_real, n_rnd, P),
+            "precision_mode": precision, "signatures_per_gpu": n_real + n_rnd,
+            "l2_policy": "inputs larger than L2 (X+W = %.1f GB per step)" % (G * N * 16 / 1e9),
+            "parallelism": "signature-block x%d" % world}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,14 +307,9 @@ def run_b200(args):
                   "consistency + median + p-values)",
         "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if precision == "fp64" else "i8 digit planes (tcgen05) + f64",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if precision == "fp64" else "f64 + u8*s8->s32 digit planes (tcgen05 kind::i8)",
         "data": "synthetic",
-        "config": {"workload": "%s: %d cells x %d genes, %d real + %d random signatures per GPU, "
-                               "%d projections, sigma=0.33" % (args.workload, N, G, n_real,
-                                                               n_rows - n_real, P),
-                   "precision_mode": precision, "signatures_per_gpu": n_rows,
-                   "l2_policy": "inputs larger than L2 (X+W = %.1f GB per step)" % (G * N * 16 / 1e9),
-                   "parallelism": "signature-block x%d" % world},
+        "config": describe_config(args.workload, cfg, n_real, n_rows - n_real, precision, world),
         "scores_per_sec": N * n_rows * world / (score_ms * 1e-3),
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_scoring": roofline_score,
@@ -476,9 +481,8 @@ def run_reference(args):
            "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * n_rows * P / value, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: %d cells x %d genes, %d real + %d random signatures, %d "
-                                  "projections, sigma=0.33" % (args.workload, N, G, len(wl["real"]),
-                                                               len(wl["rnd"]), P)},
+           "config": describe_config(args.workload, cfg, len(wl["real"]), len(wl["rnd"]),
+                                     args.precision or ("tc" if N <= 4000000 else "fp64"), args.gpus),
            "cpu_baseline": dict(last, value=value),
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
