@@ -43,6 +43,7 @@ WORKLOADS = {
     # name: genes, cells, real sigs, random sigs per size (x6 sizes), projections
     "C2": dict(G=15000, N=20000, K=500, R_PER_SIZE=500, P=6),
     "C3": dict(G=20000, N=100000, K=1000, R_PER_SIZE=500, P=8),
+    "C4": dict(G=2000, N=1000000, K=200, R_PER_SIZE=500, P=4),
     "tiny": dict(G=600, N=1024, K=24, R_PER_SIZE=10, P=2),
 }
 SIZES = [5, 10, 20, 50, 100, 200]

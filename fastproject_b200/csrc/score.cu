@@ -15,14 +15,14 @@ namespace {
 
 // Mapping: one warp = one signature x 32 consecutive cells; lanes read 256
 // contiguous bytes of a gene row (two full 128-byte lines) per operand.
-// Launch order: blockIdx.x runs over the signature tiles of ONE slab of 128
+// Launch order: blockIdx.x runs over the signature tiles of ONE slab of 32
 // cells, blockIdx.y over the slabs, so the CTAs in flight all gather from the
-// same G x 128-cell slab of X and W (30 MB at G = 15 000): it is read from HBM
+// same G x 32-cell slab of X and W (7.7 MB at G = 15 000): it is read from HBM
 // once and served from L2 to the ~15 signatures that touch each gene row.
 // (Round-1 profile of the transposed order: 73.9 GB of DRAM reads for 4.8 GB of
 // input, L2 hit rate 0.7 %.)
-constexpr int kCellsPerBlock = 128;   // blockDim.x
-constexpr int kSigsPerBlock = 4;      // blockDim.y
+constexpr int kCellsPerBlock = 32;    // blockDim.x: one warp wide -> slab of G x 32 cells (7.7 MB of X+W at G = 15 000)
+constexpr int kSigsPerBlock = 16;     // blockDim.y
 
 __device__ __forceinline__ double ldg_stream(const double *p) {
     // read-only, keep out of L1 (each value is used once by this thread)
