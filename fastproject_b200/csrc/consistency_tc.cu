@@ -444,7 +444,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             const long jbase = (long)it * KS + kchunk * 16;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();                                      // records of stage it visible; slot of it+1 free
-            if (it + 1 < n_stages) prefetch_records(it + 1);
+            if (it + 1 < n_stages && !(dbg & 32)) prefetch_records(it + 1);
             const CellJ *jr = jslot + (it & 1) * 16;
             // two halves of 8 cells j: the byte planes are packed as soon as 8 weights exist,
             // which keeps the live register set small (576 threads leave 96 registers each)
@@ -477,8 +477,9 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             uint8_t *bst = smem + s * L::stage_bytes + SR * A_PLANE_BYTES;
 #pragma unroll
             for (int a = 0; a < WD; ++a)
-                *reinterpret_cast<uint4 *>(bst + a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16) =
-                    make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
+                if (!(dbg & 64) || pk[a][0] == 0x12345u)
+                    *reinterpret_cast<uint4 *>(bst + a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16) =
+                        make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
             // weights[diag] = 0 (Signatures.py:399): the cell's own column lies in one chunk of one
             // stage; its four digit bytes are cleared after the store instead of testing every weight
             const long dj = gi - jbase;
@@ -486,7 +487,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
 #pragma unroll
                 for (int a = 0; a < WD; ++a) bst[a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16 + dj] = 0;
             }
-            fence_proxy_async_smem();
+            if (!(dbg & 16)) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bready[s]);
           }

@@ -355,3 +355,39 @@ def test_distributed_mode_single_rank_equals_local(fp):
     assert got[0] == want[0] and got[1] == want[1] and got[5] == want[5]
     for a, b in zip(got[2:5], want[2:5]):
         assert np.array_equal(a, b)
+
+
+def test_full_size_properties_of_the_tensor_core_path(fp):
+    """BASELINE config 2 cell count (20 000 cells): properties that do not need the O(N^2)
+    reference.  (1) rows are independent: a duplicated rank row gives identical output;
+    (2) the contraction is exact integer arithmetic, so permuting the cells (coordinates and
+    rank columns together) permutes the output BIT FOR BIT; (3) a constant row is predicted
+    to the precision of the digit classes; (4) medians agree with the FP64 verifier kernel on the same rows."""
+    import torch
+    from scipy.stats import rankdata
+    n, k = 20000, 12
+    rng = np.random.RandomState(77)
+    proj, _ = fp.synth.make_projections(n, 1, seed=78)
+    coords = proj["Proj00"]
+    vals = np.array([rankdata(rng.normal(size=n) + (coords[0] if r % 2 else 0)) for r in range(k)])
+    vals[5] = vals[2]                       # duplicate row
+    vals[7] = 1234.5                        # constant row
+    ld = fp.E.padded(n)
+
+    def run(c, v, precision):
+        dev = torch.zeros((v.shape[0], ld), dtype=torch.float64, device="cuda")
+        dev[:, :n] = torch.from_numpy(v).cuda()
+        out = fp.E.consistency(torch.from_numpy(np.ascontiguousarray(c)).cuda(), 0.33 ** 2, dev, n,
+                               precision=precision)
+        return out[:, :n].cpu().numpy()
+
+    base = run(coords, vals, "tc")
+    assert np.array_equal(base[5], base[2])
+    # |v - prediction| of a constant row: zero up to the uncomputed lowest digit class (2^-32 relative)
+    assert np.abs(base[7]).max() <= 1e-7 * n
+    perm = rng.permutation(n)
+    shuffled = run(coords[:, perm], vals[:, perm], "tc")
+    assert np.array_equal(shuffled, base[:, perm])
+    ref = run(coords, vals[:4], "fp64")
+    np.testing.assert_allclose(np.median(base[:4], axis=1), np.median(ref, axis=1), rtol=0, atol=2e-4)
+    assert np.abs(base[:4] - ref).max() <= 1e-7 * n
