@@ -200,10 +200,18 @@ __device__ __forceinline__ Digits decode_range(const unsigned long long *__restr
     const double mn2 = 2.0 * from_ordered_key(range[0]), mx2 = 2.0 * from_ordered_key(range[1]);
     Digits d;
     d.centre2 = floor(0.5 * (mn2 + mx2));
-    const double hr = fmax(mx2 - d.centre2, d.centre2 - mn2);
+    // + 1: room for the parity adjustment of the centre below
+    const double hr = fmax(mx2 - d.centre2, d.centre2 - mn2) + 1.0;
     d.valid = range[2] == 0ull && hr <= LIMIT;               // false for NaN / inf / too wide
     d.scale = 1.0;
-    for (int it = 0; it < 24 && 2.0 * d.scale * hr <= LIMIT && hr > 0.0; ++it) d.scale *= 2.0;
+    for (int it = 0; it < 24 && 2.0 * d.scale * hr <= LIMIT; ++it) d.scale *= 2.0;
+    // The digit products of the lowest class are not computed, so the least significant digit
+    // should average to zero over the cells.  For integer-spaced values (ranks without ties) all
+    // r = 2 v - centre2 share one parity: with scale 128 even r make that digit 0; otherwise odd
+    // r make it symmetric (e.g. +-64) where even r would give the lopsided set {0, -128}.
+    const bool want_even = d.scale == 128.0;
+    const bool is_even = fmod(mn2 - d.centre2, 2.0) == 0.0;
+    if (want_even != is_even) d.centre2 += 1.0;
     return d;
 }
 
