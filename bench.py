@@ -76,7 +76,7 @@ def parse_args():
 # ----------------------------------------------------------------------------
 # synthetic workload
 # ----------------------------------------------------------------------------
-def make_workload(cfg, device, seed=1335607828):
+def make_workload(cfg, device, seed=1335607828, sig_seed=None):
     """Synthetic inputs of SURVEY.md 8d's recipe, generated on the device for
     speed (log1p-Gamma counts with ~40 % zeros, per-gene z-score, detection
     weights), signatures on the host with the reference's RNG calls."""
@@ -104,11 +104,14 @@ def make_workload(cfg, device, seed=1335607828):
     genes = ["G%05d" % i for i in range(G)]
     cells = ["C%06d" % i for i in range(N)]
     projections, _ = synth.make_projections(N, cfg["P"], seed=seed + 1)
-    defs = synth.make_signature_dicts(genes, cfg["K"], seed=seed + 2)
+    # one data set (expression, weights, projections) for the whole job; every rank owns its
+    # own block of real + random signatures
+    sig_seed = seed if sig_seed is None else sig_seed
+    defs = synth.make_signature_dicts(genes, cfg["K"], seed=sig_seed + 2)
     real = [S.Signature(d, sg, "synthetic", nm) for nm, d, sg in defs]
     import random
-    random.seed(seed)
-    np.random.seed(seed % (2 ** 32))
+    random.seed(sig_seed)
+    np.random.seed(sig_seed % (2 ** 32))
     rnd = S.generate_random_sigs(genes, False, SIZES, cfg["R_PER_SIZE"])
     return dict(x=x, w=w, genes=genes, cells=cells, projections=projections, real=real, rnd=rnd)
 
@@ -207,7 +210,7 @@ def run_b200(args):
     cfg = WORKLOADS[args.workload]
     precision = E.resolve_precision(args.precision, cfg["N"])
     # weak scaling: every rank owns its own block of K real + R random signatures
-    wl = make_workload(cfg, device, seed=1335607828 + 7919 * rank)
+    wl = make_workload(cfg, device, seed=1335607828, sig_seed=1335607828 + 7919 * rank)
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
     x, w = wl["x"], wl["w"]
     sigs = wl["real"] + wl["rnd"]
@@ -358,8 +361,8 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5)
-        rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5)
+        real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5, distributed=world > 1)
+        rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5, distributed=world > 1)
         res = S.sigs_vs_projections(wl["projections"], real, rnd, SIGMA, precision=precision,
                                     distributed=world > 1)
         first = next(iter(real.values()))
@@ -377,11 +380,13 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     t = sum(times) / len(times)
     n_rows = len(real) + len(rnd)
     nnz = sum(len(s.sig_dict) for s in wl["real"]) + sum(len(s.sig_dict) for s in wl["rnd"])
-    h2d = 2 * G * N * 8 + nnz * 5 + (n_rows + 1) * 4 + P * 2 * N * 8
-    return {"value": world * n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * world,
+    # X and W are one data set: every rank uploads 1/world of their rows (all-gathered over NVLink)
+    h2d = 2 * G * N * 8 + world * (nnz * 5 + (n_rows + 1) * 4 + P * 2 * N * 8)
+    return {"value": world * n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h) * world, "s_per_step": t, "steps": len(times),
             "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections(distributed=%s), "
-                   "pinned host inputs, per rank" % (world > 1)}
+                   "pinned host inputs; the expression matrices are uploaded once per job (row shards "
+                   "over every rank's PCIe link + NCCL all-gather)" % (world > 1)}
 
 
 # ----------------------------------------------------------------------------

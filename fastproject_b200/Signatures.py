@@ -55,18 +55,23 @@ class Signature(object):
 
 
 def calculate_sig_scores(data, signatures, method='weighted_avg',
-                         zero_locations=None, min_signature_genes=1e99):
+                         zero_locations=None, min_signature_genes=1e99, distributed=False):
     """Signatures.py:630-681.  All signatures (real or random background) are
     scored by ONE kernel launch on the device-resident expression / weight
     matrices; signatures matching no gene or fewer than ``min_signature_genes``
     genes are silently discarded as in the reference (:672-676).
 
     Returns dict name -> SignatureScores (insertion-ordered).  The score vectors
-    stay on the GPU until ``.scores`` / ``.ranks`` is read."""
+    stay on the GPU until ``.scores`` / ``.ranks`` is read.
+
+    ``distributed`` (extension): one process per GPU, every rank passes the SAME expression data
+    and ITS block of signatures; the matrices are then uploaded cooperatively (1/world of the
+    rows per PCIe link, all-gathered over NVLink)."""
     if method not in _scoring.METHODS:
         # the reference leaves sig_score_method unbound here (UnboundLocalError)
         raise UnboundLocalError("unknown signature score method %r" % (method,))
-    batch = _scoring.score_batch(data, signatures, method, zero_locations, min_signature_genes)
+    batch = _scoring.score_batch(data, signatures, method, zero_locations, min_signature_genes,
+                                 replicated=distributed)
     sig_scores_dict = dict()
     for row, pos in enumerate(batch.kept):
         sig = signatures[pos]

@@ -69,6 +69,37 @@ def to_device(arr, dtype=torch.float64):
     return t.contiguous()
 
 
+def to_device_replicated(arr):
+    """Upload a matrix that is identical on every rank: rank r copies rows
+    [r*rows_per, (r+1)*rows_per) host -> device, then one NCCL all-gather assembles the whole
+    matrix on every GPU.  The PCIe traffic per GPU is 1/world of the matrix."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return to_device(arr)
+    dev = require_cuda()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if isinstance(arr, torch.Tensor):
+        host = arr
+    else:
+        a = np.asarray(arr)
+        if a.dtype == np.bool_:
+            a = a.astype(np.float64)
+        if not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a)
+        host = torch.from_numpy(a)
+    rows, cols = host.shape
+    rows_per = (rows + world - 1) // world
+    full = torch.empty((world * rows_per, cols), dtype=torch.float64, device=dev)
+    lo, hi = min(rows, rank * rows_per), min(rows, (rank + 1) * rows_per)
+    mine = full[rank * rows_per:(rank + 1) * rows_per]
+    if hi > lo:
+        mine[:hi - lo].copy_(host[lo:hi], non_blocking=True)
+    if hi - lo < rows_per:
+        mine[hi - lo:].zero_()
+    dist.all_gather_into_tensor(full, mine.clone() if world > 1 else mine)
+    return full[:rows]
+
+
 class _ExpressionCache(object):
     """Keeps the last few genes x cells matrices resident in HBM so that the
     two calculate_sig_scores calls of the pipeline (real, then random
@@ -103,17 +134,21 @@ class _ExpressionCache(object):
         sample = a.reshape(-1)[idx] if a.flags["C_CONTIGUOUS"] else a.T.reshape(-1)[idx]
         return np.ascontiguousarray(sample).tobytes()
 
-    def get(self, a):
+    def get(self, a, replicated=False):
+        """``replicated``: every rank of the process group holds the same host matrix (the
+        expression data of a multi-GPU run); each rank then uploads 1/world of the rows over
+        its own PCIe link and the rows are all-gathered over NVLink."""
+        upload = to_device_replicated if replicated else to_device
         if isinstance(a, torch.Tensor) and a.is_cuda:
             return a.to(torch.float64).contiguous()
         if os.environ.get("FASTPROJECT_B200_NO_CACHE"):
-            return to_device(a)
+            return upload(a)
         key, fp = self._key(a), self._fingerprint(a)
         for i, (k, f, t) in enumerate(self.entries):
             if k == key and f == fp:
                 self.entries.append(self.entries.pop(i))
                 return t
-        t = to_device(a)
+        t = upload(a)
         self.entries.append((key, fp, t))
         while len(self.entries) > self.capacity:
             self.entries.pop(0)

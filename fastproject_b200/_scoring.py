@@ -124,7 +124,7 @@ def _matrix_of(data):
 
 
 def score_batch(data, signatures, method, zero_locations, min_signature_genes,
-                raise_on_reject=False):
+                raise_on_reject=False, replicated=False):
     """Score ``signatures`` on ``data``; returns a ScoreBatch whose ``kept``
     lists the positions (into ``signatures``) that survived."""
     if method not in METHODS:
@@ -132,17 +132,17 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
     kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
         signatures, data.row_labels, min_signature_genes, raise_on_reject)
     _engine.require_cuda()
-    x = _engine.expression_cache.get(_matrix_of(data))
+    x = _engine.expression_cache.get(_matrix_of(data), replicated)
     n_genes, n_cells = x.shape
     w = z = None
     if method in ("weighted_avg", "imputed"):
-        w = _engine.expression_cache.get(data.weights)
+        w = _engine.expression_cache.get(data.weights, replicated)
         if tuple(w.shape) != (n_genes, n_cells):
             raise ValueError("weights shape %s != data shape %s" % (tuple(w.shape), (n_genes, n_cells)))
     if method in ("imputed", "only_nonzero"):
         if zero_locations is None:
             raise TypeError("method %r needs zero_locations" % method)
-        z = _engine.expression_cache.get(zero_locations)
+        z = _engine.expression_cache.get(zero_locations, replicated)
     d_ptr = _engine.to_device(sig_ptr, torch.int32)
     d_gene = _engine.to_device(sig_gene, torch.int32)
     d_sign = _engine.to_device(sig_sign, torch.int8)
