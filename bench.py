@@ -332,7 +332,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
 
 
 def run_e2e(args, cfg, wl, precision, world=1, device=None):
@@ -492,10 +492,28 @@ def run_reference(args):
            "cpu_baseline": dict(last, value=value),
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract goes to the real stdout; everything else that writes
+    to fd 1 (NCCL's version banner, progress bars of the mirrored API) was sent to stderr."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
