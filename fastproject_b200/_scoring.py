@@ -5,6 +5,8 @@
 ``ScoreBatch`` and its lazy host views."""
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 import torch
 
@@ -62,8 +64,50 @@ def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject
     """list[Signature] -> (kept positions, sig_ptr, sig_gene, sig_sign, num_genes).
     Signatures with no matched gene, or fewer than ``min_signature_genes``, are
     rejected -- the reference raises ValueError for them
-    (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676)."""
+    (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676).
+
+    All signatures are matched in one vectorised pass (C-level ``map`` over the
+    concatenated gene lists, one ``lexsort``); duplicated row labels take the
+    per-signature path."""
     index = gene_row_index(row_labels)
+    if len(index) != len(row_labels) or raise_on_reject or len(signatures) < 8:
+        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+    dicts = [sig.sig_dict for sig in signatures]
+    lengths = np.fromiter((len(d) for d in dicts), dtype=np.int64, count=len(dicts))
+    flat_genes = list(itertools.chain.from_iterable(dicts))
+    flat_vals = list(itertools.chain.from_iterable(d.values() for d in dicts))
+    rows = np.fromiter(map(index.get, flat_genes, itertools.repeat(-1)), dtype=np.int64,
+                       count=len(flat_genes))
+    try:
+        vals = np.fromiter(flat_vals, dtype=np.float64, count=len(flat_vals))
+    except (TypeError, ValueError):
+        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+    # a dict value equal to 1 or 0 counts as +1, equal to -1 as -1, anything else is ignored
+    signs = np.where((vals == 1) | (vals == 0), 1, np.where(vals == -1, -1, 0)).astype(np.int8)
+    sig_id = np.repeat(np.arange(len(dicts), dtype=np.int64), lengths)
+    ok = (rows >= 0) & (signs != 0)
+    rows, signs, sig_id = rows[ok], signs[ok], sig_id[ok]
+    counts_all = np.bincount(sig_id, minlength=len(dicts)).astype(np.int64)
+    keep_sig = (counts_all > 0) & (counts_all >= min_signature_genes)
+    entry_ok = keep_sig[sig_id]
+    rows, signs, sig_id = rows[entry_ok], signs[entry_ok], sig_id[entry_ok]
+    # by signature, ascending gene row inside: one sort of a combined key carrying the sign bit
+    n_rows_total = len(row_labels)
+    key = np.sort((sig_id * n_rows_total + rows) * 2 + (signs > 0))
+    signs = np.where(key & 1, 1, -1).astype(np.int8)
+    rows = (key >> 1) % n_rows_total
+    order = slice(None)
+    kept = np.nonzero(keep_sig)[0]
+    counts = counts_all[kept]
+    ptr = np.zeros(len(kept) + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    if ptr[-1] >= 2 ** 31:
+        raise ValueError("signature membership table exceeds int32 indexing")
+    return ([int(k) for k in kept], ptr.astype(np.int32), rows[order].astype(np.int32),
+            signs[order].astype(np.int8), counts)
+
+
+def _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject=False):
     kept, ptr, genes, signs, counts = [], [0], [], [], []
     for pos, sig in enumerate(signatures):
         rows, sg = signature_rows(sig.sig_dict, index)
@@ -129,9 +173,9 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
     lists the positions (into ``signatures``) that survived."""
     if method not in METHODS:
         raise KeyError(method)
-    kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
-        signatures, data.row_labels, min_signature_genes, raise_on_reject)
     _engine.require_cuda()
+    # the (asynchronous, pinned-memory) uploads are enqueued first so that the host-side CSR
+    # packing below runs while the matrices cross PCIe
     x = _engine.expression_cache.get(_matrix_of(data), replicated)
     n_genes, n_cells = x.shape
     w = z = None
@@ -143,6 +187,8 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
         if zero_locations is None:
             raise TypeError("method %r needs zero_locations" % method)
         z = _engine.expression_cache.get(zero_locations, replicated)
+    kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
+        signatures, data.row_labels, min_signature_genes, raise_on_reject)
     d_ptr = _engine.to_device(sig_ptr, torch.int32)
     d_gene = _engine.to_device(sig_gene, torch.int32)
     d_sign = _engine.to_device(sig_sign, torch.int8)
