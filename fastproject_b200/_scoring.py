@@ -151,12 +151,12 @@ class ScoreBatch(object):
 
     def host_scores(self):
         if self._host_scores is None:
-            self._host_scores = self.scores_dev[:, :self.n_cells].cpu().numpy()
+            self._host_scores = _engine.to_host(self.scores_dev[:, :self.n_cells])
         return self._host_scores
 
     def host_ranks(self):
         if self._host_ranks is None:
-            self._host_ranks = self.ranks_dev()[:, :self.n_cells].cpu().numpy()
+            self._host_ranks = _engine.to_host(self.ranks_dev()[:, :self.n_cells])
         return self._host_ranks
 
 
