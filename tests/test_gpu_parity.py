@@ -343,9 +343,12 @@ def test_distributed_mode_single_rank_equals_local(fp):
     want = _svp(fp, c, precision="fp64")
     created = False
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl", rank=0, world_size=1)
+        import socket
+        sock = socket.socket()
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+        sock.close()
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
         created = True
     try:
         got = _svp(fp, c, precision="fp64", distributed=True)
