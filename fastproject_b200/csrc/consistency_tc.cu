@@ -289,6 +289,31 @@ __device__ __forceinline__ uint32_t weight_fixed32(double t, const char *__restr
     return (uint32_t)__double2loint(vs + 4503599627370496.0);   // + 2^52: round to integer
 }
 
+// The MMAs of one K step (32 cells j): every (weight digit a, value digit b) pair with
+// a + b < NCLASS, accumulated into class a + b.  Descriptors differ from the step's base
+// descriptors by compile-time constants (plane offsets) and the accumulate flags are
+// compile-time too, so the issuing thread executes little more than the MMAs themselves --
+// with run-time flags and descriptor arithmetic it needed 336 instructions per stage and
+// issued slower (93 clk per MMA) than the tensor core executes (64 clk).
+template <int SR, bool OPEN_CLASSES>
+__device__ __forceinline__ void issue_k_step(uint32_t tmem, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc) {
+#pragma unroll
+    for (int a = 0; a < WD; ++a)
+#pragma unroll
+        for (int b = 0; b < SR; ++b) {
+            const int c = a + b;                  // value digit 0 = most significant
+            if (c >= NCLASS) continue;
+            // first product written to a class: (0, c) for c < SR, else (c-SR+1, SR-1)
+            const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
+            const uint64_t ad = a_desc0 + (uint64_t)(b * (A_PLANE_BYTES >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(a * (B_PLANE_BYTES >> 4));
+            if (OPEN_CLASSES && opens)
+                umma_i8_pair_c<0>(tmem + c * TN, ad, bd, idesc);
+            else
+                umma_i8_pair_c<1>(tmem + c * TN, ad, bd, idesc);
+        }
+}
+
 template <int SR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const CellI *__restrict__ ci,
@@ -342,6 +367,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
             for (int it = 0; it < n_stages; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
+                if (dbg & 128) mbar_spin(&empty[s], ph ^ 1); else
                 mbar_wait(&empty[s], ph ^ 1);
                 if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * SR * A_PLANE_BYTES);
                 const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
@@ -368,6 +394,8 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
         // ------------------------------------------------ MMA issuer (leader CTA)
         if (rank == 0) {
             const uint32_t idesc = idesc_i8(2 * TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
+            const uint64_t a_desc_base = smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
+            const uint64_t b_desc_base = smem_desc(smem_u32(smem) + SR * A_PLANE_BYTES, TNH * 16, 128, LAYOUT_NONE);
             for (int it = 0; it < n_stages; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -377,35 +405,28 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                     mbar_wait_cluster(tmem_empty, (chunk - 1) & 1);     // epilogues of both CTAs drained TMEM
                     tc_fence_after_sync();
                 }
+                if (dbg & 128) {
+                    mbar_spin(&bready[s], ph);
+                    mbar_spin_cluster(&full[s], ph);
+                } else {
                 mbar_wait(&bready[s], ph);                    // own generators
                 mbar_wait_cluster(&full[s], ph);              // value planes of both CTAs + the peer's weights
+                }
                 tc_fence_after_sync();
-                if (lane == 0) {
-                    const uint32_t a_base = smem_u32(smem + s * L::stage_bytes);
-                    const uint32_t b_base = a_base + SR * A_PLANE_BYTES;
+                if (elect_one()) {
+                    const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                    const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                    if (!(dbg & 1)) {
+                        // K step ks: 32 bytes further along the swizzled A rows, two 16-byte chunks
+                        // (2 * TNH * 16 bytes) further in the B planes
+                        if (chunk_first)
+                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
+                        else
+                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
 #pragma unroll
-                    for (int ks = 0; ks < KS / 32; ++ks) {
-                        uint64_t ad[SR], bd[WD];
-#pragma unroll
-                        for (int b = 0; b < SR; ++b)
-                            ad[b] = smem_desc(a_base + b * A_PLANE_BYTES + ks * 32, 16, 1024, LAYOUT_SW128);
-#pragma unroll
-                        for (int a = 0; a < WD; ++a)
-                            bd[a] = smem_desc(b_base + a * B_PLANE_BYTES + ks * 2 * TNH * 16, TNH * 16, 128,
-                                              LAYOUT_NONE);
-                        const uint32_t first = (chunk_first && ks == 0) ? 0u : 1u;
-                        // class c = (weight digit a) + (value digit b), value digit 0 = most significant
-#pragma unroll
-                        for (int a = 0; a < WD; ++a)
-#pragma unroll
-                            for (int b = 0; b < SR; ++b) {
-                                const int c = a + b;
-                                if (c >= NCLASS) continue;
-                                // first product written to a class: (0, c) for c < SR, else (c-SR+1, SR-1)
-                                const bool opens = (a == 0) || (b == SR - 1 && c >= SR);
-                                if (!(dbg & 1))
-                                    umma_i8_pair(tmem + c * TN, ad[b], bd[a], idesc, opens ? first : 1u);
-                            }
+                        for (int ks = 1; ks < KS / 32; ++ks)
+                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * (2 * TNH)),
+                                                    idesc);
                     }
                     umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
                     if (it % chunk_stages == chunk_stages - 1 || it == n_stages - 1) umma_commit_pair(accum_full);
@@ -481,6 +502,7 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                     pk[a][2 * h + 1] = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
                 }
             }
+            if (dbg & 128) mbar_spin(&empty[s], ph ^ 1); else
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t *bst = smem + s * L::stage_bytes + SR * A_PLANE_BYTES;
 #pragma unroll
