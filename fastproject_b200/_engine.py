@@ -222,15 +222,33 @@ def score_signatures(method, x, w, z, sig_ptr, sig_gene, sig_sign, n_sigs):
     return out
 
 
-def rank_rows(scores, n):
-    """scores: [K x ld] CUDA float64 -> average ranks, same shape."""
+def rank_rows(scores, n, method=_native.RANK_AVERAGE):
+    """scores: [K x ld] CUDA float64 -> ranks of every row (average or min tie rule), same shape."""
     k, ld = scores.shape
     out = torch.zeros_like(scores)
     if k == 0:
         return out
     nbytes = _native.query("fp_rank_workspace_bytes", k, n, ld)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=scores.device)
-    _native.call("fp_rank_columns", ptr(scores), k, n, ld, ptr(out), ptr(ws), nbytes, stream_ptr())
+    _native.call("fp_rank_columns_ex", ptr(scores), k, n, ld, ptr(out), ptr(ws), nbytes, method, stream_ptr())
+    return out
+
+
+def normalize_rows(x):
+    """[G x N] CUDA float64 -> per-row z-scores (NumPy summation order), new tensor."""
+    g, n = x.shape
+    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
+    nbytes = _native.query("fp_normalize_rows_workspace_bytes", n)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _native.call("fp_normalize_rows", ptr(x), g, n, x.stride(0), ptr(out), n, ptr(ws), nbytes, stream_ptr())
+    return out
+
+
+def normalize_cols(x):
+    """[G x N] CUDA float64 -> per-column z-scores (sequential row order), new tensor."""
+    g, n = x.shape
+    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
+    _native.call("fp_normalize_cols", ptr(x), g, n, x.stride(0), ptr(out), n, stream_ptr())
     return out
 
 

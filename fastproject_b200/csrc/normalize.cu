@@ -1,0 +1,188 @@
+// Data normalisation before signature scoring -- the step right before the hot path
+// (SURVEY.md 8f, row N1).  Replaces /root/reference/FastProject/NormalizationMethods.py:
+//   row_normalization (:34-41, the CLI default "znorm_rows"), col_normalization (:24-31);
+// row_and_col_normalization (:44-50) is the two applied in turn by the Python mirror and
+// col_rank_normalization (:53-61) goes through fp_rank_columns_ex (method "min").
+//
+// Bit-exactness contract.  NumPy computes
+//   mu    = add.reduce(x, axis) / n
+//   sigma = sqrt(add.reduce((x - mu) * (x - mu), axis) / n),   sigma == 0 -> 1
+//   out   = (x - mu) / sigma
+// where add.reduce along the CONTIGUOUS axis (rows, axis=1) is NumPy's pairwise summation
+// (blocks of <= 128 elements with eight interleaved accumulators, halves combined
+// recursively) and along axis=0 it is a plain sequential sum over the rows.  Both orders are
+// reproduced, every operation separately rounded, so the result equals the reference's bit
+// for bit.
+//
+// Row kernel: one CTA per gene.  The leaves of the pairwise tree (it depends on N only; the
+// host enumerates it once per call) are summed by one thread each -- a leaf is 1 KB of
+// consecutive doubles, so a warp streams 32 leaves through L1 -- and thread 0 folds the leaf
+// sums with the tree's post-order program.
+#include <vector>
+
+#include "fp_common.cuh"
+
+namespace {
+
+struct Leaf {
+    int lo, n;
+};
+
+struct RowLoad {
+    const double *x;
+    __device__ double operator()(long i) const { return x[i]; }
+};
+struct RowSqDev {
+    const double *x;
+    double mean;
+    __device__ double operator()(long i) const {
+        const double d = __dsub_rn(x[i], mean);
+        return __dmul_rn(d, d);
+    }
+};
+
+// post-order program: entry >= 0 pushes the sum of that leaf, -1 pops two and pushes their sum
+__device__ double fold_tree(const double *leaf_sum, const int *__restrict__ prog, int n_prog, double *stack) {
+    int sp = 0;
+    for (int p = 0; p < n_prog; ++p) {
+        const int op = prog[p];
+        if (op >= 0) {
+            stack[sp++] = leaf_sum[op];
+        } else {
+            const double b = stack[--sp], a = stack[--sp];
+            stack[sp++] = __dadd_rn(a, b);
+        }
+    }
+    return stack[0];
+}
+
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_DEPTH = 48;
+
+__global__ void __launch_bounds__(ROW_THREADS)
+row_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out,
+                  const Leaf *__restrict__ leaves, int n_leaves, const int *__restrict__ prog, int n_prog) {
+    extern __shared__ double leaf_sum[];                 // n_leaves
+    __shared__ double stack[MAX_DEPTH];
+    __shared__ double stat[2];
+    for (long g = blockIdx.x; g < G; g += gridDim.x) {
+        const double *row = X + g * ld;
+        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
+            leaf_sum[l] = fp::np_pairwise_sum(RowLoad{row}, leaves[l].lo, leaves[l].n);
+        __syncthreads();
+        if (threadIdx.x == 0) stat[0] = __ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N);
+        __syncthreads();
+        const double mean = stat[0];
+        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
+            leaf_sum[l] = fp::np_pairwise_sum(RowSqDev{row, mean}, leaves[l].lo, leaves[l].n);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sd = sqrt(__ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N));
+            if (sd == 0.0) sd = 1.0;                      // data_sigma[data_sigma == 0] = 1.0
+            stat[1] = sd;
+        }
+        __syncthreads();
+        const double sd = stat[1];
+        double *orow = out + g * ld_out;
+        for (long c = threadIdx.x; c < N; c += blockDim.x) orow[c] = __ddiv_rn(__dsub_rn(row[c], mean), sd);
+        __syncthreads();
+    }
+}
+
+// axis = 0: plain sequential sums over the rows, one thread per column (coalesced)
+__global__ void __launch_bounds__(128)
+col_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double s = 0.0;
+    for (long g = 0; g < G; ++g) s = __dadd_rn(s, X[g * ld + c]);
+    const double mean = __ddiv_rn(s, (double)G);
+    double s2 = 0.0;
+    for (long g = 0; g < G; ++g) {
+        const double d = __dsub_rn(X[g * ld + c], mean);
+        s2 = __dadd_rn(s2, __dmul_rn(d, d));
+    }
+    double sd = sqrt(__ddiv_rn(s2, (double)G));
+    if (sd == 0.0) sd = 1.0;
+    for (long g = 0; g < G; ++g) out[g * ld_out + c] = __ddiv_rn(__dsub_rn(X[g * ld + c], mean), sd);
+}
+
+// NumPy's pairwise_sum recursion (numpy/_core/src/umath/loops_utils.h.src): n > 128 splits at
+// n/2 rounded down to a multiple of 8
+void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
+    if (depth > max_depth) max_depth = depth;
+    if (n <= 128) {
+        prog.push_back((int)leaves.size());
+        leaves.push_back(Leaf{(int)lo, (int)n});
+        return;
+    }
+    long n2 = n / 2;
+    n2 -= n2 % 8;
+    build_tree(lo, n2, leaves, prog, depth + 1, max_depth);
+    build_tree(lo + n2, n - n2, leaves, prog, depth + 1, max_depth);
+    prog.push_back(-1);
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t fp_normalize_rows_workspace_bytes(int64_t N) {
+    if (N <= 0) return 0;
+    const size_t max_leaves = (size_t)(N / 32 + 2);
+    return align_up(max_leaves * sizeof(Leaf)) + align_up(2 * max_leaves * sizeof(int)) + 256;
+}
+
+extern "C" int fp_normalize_rows(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(X && out, "fp_normalize_rows: null pointer");
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N, "fp_normalize_rows: bad shape G=%ld N=%ld", (long)G,
+                 (long)N);
+    FP_CHECK_ARG(N < (1L << 31), "fp_normalize_rows: N too large");
+    std::vector<Leaf> leaves;
+    std::vector<int> prog;
+    int max_depth = 0;
+    build_tree(0, N, leaves, prog, 1, max_depth);
+    if (max_depth + 1 > MAX_DEPTH || leaves.size() * 8 > 200 * 1024) {
+        fp::set_error("fp_normalize_rows: rows of %ld cells need %zu tree leaves (limit 25600)", (long)N,
+                      leaves.size());
+        return FP_EUNSUPPORTED;
+    }
+    const size_t leaves_b = align_up(leaves.size() * sizeof(Leaf)), prog_b = align_up(prog.size() * sizeof(int));
+    if (!workspace || workspace_bytes < leaves_b + prog_b) {
+        fp::set_error("fp_normalize_rows: workspace %zu bytes < required %zu", workspace_bytes, leaves_b + prog_b);
+        return FP_EWORKSPACE;
+    }
+    cudaStream_t st = fp::as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    FP_CHECK_CUDA(cudaMemcpyAsync(ws, leaves.data(), leaves.size() * sizeof(Leaf), cudaMemcpyHostToDevice, st));
+    FP_CHECK_CUDA(cudaMemcpyAsync(ws + leaves_b, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    FP_CHECK_CUDA(cudaStreamSynchronize(st));          // the host vectors die at return
+    const size_t smem = leaves.size() * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > 40 * 1024 && smem > smem_set) {
+        FP_CHECK_CUDA(cudaFuncSetAttribute(row_zscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        smem_set = smem;
+    }
+    long blocks = G;
+    const long cap = (long)fp::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    row_zscore_kernel<<<(unsigned)blocks, ROW_THREADS, smem, st>>>(
+        X, G, N, ld, out, ld_out, reinterpret_cast<const Leaf *>(ws), (int)leaves.size(),
+        reinterpret_cast<const int *>(ws + leaves_b), (int)prog.size());
+    FP_CHECK_LAUNCH("row_zscore_kernel");
+    return FP_OK;
+}
+
+extern "C" int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,
+                                 void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(X && out, "fp_normalize_cols: null pointer");
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N, "fp_normalize_cols: bad shape G=%ld N=%ld", (long)G,
+                 (long)N);
+    col_zscore_kernel<<<(unsigned)((N + 127) / 128), 128, 0, fp::as_stream(stream)>>>(X, G, N, ld, out, ld_out);
+    FP_CHECK_LAUNCH("col_zscore_kernel");
+    return FP_OK;
+}

@@ -49,7 +49,7 @@ __global__ void fill_cell_index_kernel(int32_t *__restrict__ idx, long rows, lon
 __global__ void __launch_bounds__(256)
 assign_average_ranks_kernel(const double *__restrict__ sorted_keys,
                             const int32_t *__restrict__ sorted_cell, long rows, long N, long ld,
-                            double *__restrict__ out_ranks, long ld_out) {
+                            double *__restrict__ out_ranks, long ld_out, int method) {
   for (long row = blockIdx.y; row < rows; row += gridDim.y) {
     const double *ks = sorted_keys + row * ld;
     const int32_t *cs = sorted_cell + row * ld;
@@ -80,7 +80,8 @@ assign_average_ranks_kernel(const double *__restrict__ sorted_keys,
                     if (ks[mid] > v) hi = mid; else lo = mid + 1;
                 }
                 const long b = lo;
-                rank = 0.5 * (double)(a + b + 1);    // mean of ranks a+1 .. b (exact)
+                // "average": mean of ranks a+1 .. b (exact); "min": the smallest of them
+                rank = method == FP_RANK_MIN ? (double)(a + 1) : 0.5 * (double)(a + b + 1);
             }
         }
         out[cs[p]] = rank;
@@ -119,10 +120,19 @@ extern "C" size_t fp_rank_workspace_bytes(int64_t K, int64_t N, int64_t ld) {
            align_up(cub_temp_bytes(rows, N, ld)) + 1024;
 }
 
+extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld, double *out_ranks,
+                                  void *workspace, size_t workspace_bytes, int method, void *stream);
+
 extern "C" int fp_rank_columns(const double *scores, int64_t K, int64_t N, int64_t ld,
                                double *out_ranks, void *workspace, size_t workspace_bytes,
                                void *stream) {
+    return fp_rank_columns_ex(scores, K, N, ld, out_ranks, workspace, workspace_bytes, FP_RANK_AVERAGE, stream);
+}
+
+extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld, double *out_ranks,
+                                  void *workspace, size_t workspace_bytes, int method, void *stream) {
     fp::clear_error();
+    FP_CHECK_ARG(method == FP_RANK_AVERAGE || method == FP_RANK_MIN, "fp_rank_columns: unknown method %d", method);
     FP_CHECK_ARG(scores && out_ranks, "fp_rank_columns: null pointer");
     FP_CHECK_ARG(K >= 0 && N > 0 && ld >= N, "fp_rank_columns: bad shape K=%ld N=%ld ld=%ld",
                  (long)K, (long)N, (long)ld);
@@ -160,7 +170,7 @@ extern "C" int fp_rank_columns(const double *scores, int64_t K, int64_t N, int64
         if (gx > 64) gx = 64;
         const unsigned gy = (unsigned)(nb < 32768 ? nb : 32768);
         assign_average_ranks_kernel<<<dim3(gx, gy), 256, 0, st>>>(
-            keys_sorted, cell_sorted, nb, N, ld, out_ranks + k0 * ld, ld);
+            keys_sorted, cell_sorted, nb, N, ld, out_ranks + k0 * ld, ld, method);
         FP_CHECK_LAUNCH("assign_average_ranks_kernel");
     }
     return FP_OK;

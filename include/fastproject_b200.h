@@ -121,10 +121,31 @@ int fp_score_signatures(int method,
  * the matrix assembly of Signatures.py:359-369.
  *   scores, out_ranks : K x ld float64 (may not alias)
  */
+#define FP_RANK_AVERAGE 0   /* scipy rankdata(method="average"): SignatureScores.ranks          */
+#define FP_RANK_MIN     1   /* scipy rankdata(method="min"): NormalizationMethods.py:53-61      */
 size_t fp_rank_workspace_bytes(int64_t K, int64_t N, int64_t ld);
 int fp_rank_columns(const double *scores, int64_t K, int64_t N, int64_t ld,
                     double *out_ranks, void *workspace, size_t workspace_bytes,
                     void *stream);
+
+/* same with the tie rule selectable (FP_RANK_*); rows are ranked independently */
+int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld,
+                       double *out_ranks, void *workspace, size_t workspace_bytes,
+                       int method, void *stream);
+
+/*
+ * fp_normalize_rows / fp_normalize_cols -- z-normalisation of every gene (row) or every
+ * cell (column) of the genes x cells matrix: (x - mean) / std with population std and
+ * std == 0 -> 1.  Replace NormalizationMethods.row_normalization (:34-41, the pipeline
+ * default applied at Pipelines.py:202) and col_normalization (:24-31); the sums follow
+ * NumPy's order (pairwise along rows, sequential along columns), so the output is
+ * bit-identical to the reference.  out may not alias X.
+ */
+size_t fp_normalize_rows_workspace_bytes(int64_t N);
+int fp_normalize_rows(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,
+                      void *stream);
 
 /*
  * fp_consistency -- for one projection, the local dissimilarity

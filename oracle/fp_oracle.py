@@ -29,6 +29,8 @@ Reference lines followed (relative to /root/reference/FastProject/):
   sigs_vs_projections .............. Signatures.py:300-534
   get_bg_dist ...................... Signatures.py:19-27
   p_to_q ........................... Signatures.py:536-551
+  row/col/row_and_col/col_rank normalisation (the "next" row N1)
+  .................................. NormalizationMethods.py:17-61
 The arithmetic itself lives in numpy / scipy (rankdata, cdist, norm.cdf),
 which are not vendored by the reference (setup.py:19-20 pins only lower
 bounds); the golden files record the versions they were generated with.
@@ -441,6 +443,27 @@ def row_normalization(data):
     sd = data.std(axis=1, keepdims=True)
     sd[sd == 0] = 1.0
     return (data - mu) / sd
+
+
+def col_normalization(data):
+    """NormalizationMethods.py:24-31 -- per-cell z-score (sigma 0 -> 1)."""
+    mu = data.mean(axis=0, keepdims=True)
+    sd = data.std(axis=0, keepdims=True)
+    sd[sd == 0] = 1.0
+    return (data - mu) / sd
+
+
+def row_and_col_normalization(data):
+    """NormalizationMethods.py:44-50 -- rows, then columns."""
+    return col_normalization(row_normalization(data))
+
+
+def col_rank_normalization(data):
+    """NormalizationMethods.py:53-61 -- column-wise ranks, ties take the smallest rank."""
+    out = np.zeros(data.shape)
+    for i in range(data.shape[1]):
+        out[:, i] = rankdata(data[:, i], method="min")
+    return out
 
 
 def normalize_projection(xy):

@@ -269,7 +269,27 @@ def randsig_case():
     return out
 
 
+def norm_case():
+    """NormalizationMethods.py on a small matrix with a constant gene, a constant cell, ties,
+    and a long row (pairwise summation splits above 128 elements)."""
+    from FastProject import NormalizationMethods as RefNorm
+    rng = np.random.RandomState(RANDOM_SEED % (2 ** 32))
+    out = dict(versions())
+    for tag, shape in (("small", (23, 37)), ("wide", (9, 1237))):
+        x = np.log1p(rng.gamma(0.5, 4.0, size=shape)) * (rng.uniform(size=shape) < 0.6)
+        x[3, :] = 2.5                      # constant gene: sigma 0 -> 1
+        if tag == "small":
+            x[:, 5] = 0.0                  # constant cell
+        out[tag + "_X"] = x
+        out[tag + "_rows"] = RefNorm.row_normalization(x.copy())
+        out[tag + "_cols"] = RefNorm.col_normalization(x.copy())
+        out[tag + "_rows_cols"] = RefNorm.row_and_col_normalization(x.copy())
+        out[tag + "_col_rank"] = RefNorm.col_rank_normalization(x.copy())
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "case_norm.npz"), **norm_case())
     np.savez_compressed(os.path.join(HERE, "case_synth_odd.npz"),
                         **synth_case(240, 65, 3, 1001, True, False))
     np.savez_compressed(os.path.join(HERE, "case_synth_even.npz"),

@@ -394,3 +394,42 @@ def test_full_size_properties_of_the_tensor_core_path(fp):
     ref = run(coords, vals[:4], "fp64")
     np.testing.assert_allclose(np.median(base[:4], axis=1), np.median(ref, axis=1), rtol=0, atol=2e-4)
     assert np.abs(base[:4] - ref).max() <= 1e-7 * n
+
+
+# ------------------------------------------------------------------ normalisation (next row N1)
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_normalization_methods_bit_exact_vs_reference_golden(fp, tag):
+    from fastproject_b200 import NormalizationMethods as NM
+    c = G.load("case_norm")
+    x = c[tag + "_X"]
+    assert NM.no_normalization(x) is x
+    assert np.array_equal(NM.row_normalization(x.copy()), c[tag + "_rows"])
+    assert np.array_equal(NM.col_normalization(x.copy()), c[tag + "_cols"])
+    assert np.array_equal(NM.row_and_col_normalization(x.copy()), c[tag + "_rows_cols"])
+    assert np.array_equal(NM.col_rank_normalization(x.copy()), c[tag + "_col_rank"])
+
+
+def test_normalization_midsize_bit_exact_vs_oracle_and_device_path(fp):
+    """20 000 cells per gene (the pairwise tree is 8 levels deep), F-ordered input, and the
+    device-resident variant feeding calculate_sig_scores without a host round trip."""
+    import torch
+    from fastproject_b200 import NormalizationMethods as NM
+    rng = np.random.RandomState(5)
+    x = np.log1p(rng.gamma(0.5, 4.0, size=(64, 20000))) * (rng.uniform(size=(64, 20000)) < 0.6)
+    x[7] = 0.0
+    assert np.array_equal(NM.row_normalization(x), O.row_normalization(x))
+    assert np.array_equal(NM.col_normalization(x), O.col_normalization(x))
+    assert np.array_equal(NM.row_normalization(np.asfortranarray(x)), O.row_normalization(x))
+    small = x[:, :257]
+    assert np.array_equal(NM.col_rank_normalization(small), O.col_rank_normalization(small))
+    dev = NM.row_normalization(torch.from_numpy(x).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), O.row_normalization(x))
+    genes = ["g%d" % i for i in range(64)]
+    cells = ["c%d" % i for i in range(20000)]
+    sig = fp.S.Signature(dict((g, 1) for g in genes[:20]), False, "t", "s")
+    w = np.ones_like(x)
+    got = fp.S.calculate_sig_scores(fp.synth.ExpressionMatrix(dev, torch.from_numpy(w).cuda(), genes, cells),
+                                    [sig] * 1, "weighted_avg", None, 5)
+    want = O.calculate_sig_scores(O.ExpressionMatrix(O.row_normalization(x), w, genes, cells),
+                                  [O.Signature(sig.sig_dict, False, "t", "s")], "weighted_avg", None, 5)
+    assert np.array_equal(got["s"].scores, want["s"].scores)

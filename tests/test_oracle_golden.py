@@ -108,3 +108,14 @@ def test_generate_random_sigs_rng_streams():
 def test_p_to_q():
     c = G.load("case_randsigs")
     assert np.array_equal(O.p_to_q(c["p_in"].copy()), c["q_out"])
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_normalization_methods_bit_exact(tag):
+    """Oracle restatement of NormalizationMethods.py against outputs of the live reference."""
+    c = G.load("case_norm")
+    x = c[tag + "_X"]
+    assert np.array_equal(O.row_normalization(x.copy()), c[tag + "_rows"])
+    assert np.array_equal(O.col_normalization(x.copy()), c[tag + "_cols"])
+    assert np.array_equal(O.row_and_col_normalization(x.copy()), c[tag + "_rows_cols"])
+    assert np.array_equal(O.col_rank_normalization(x.copy()), c[tag + "_col_rank"])
