@@ -12,12 +12,12 @@ ABI of ``include/fastproject_b200.h``; there is no CPU fallback.
 from . import Global  # noqa: F401  (seeds the global ``random`` stream like the reference)
 
 __version__ = "0.1.0"
-__all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Global", "synth"]
+__all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Interactive", "Global", "synth"]
 
 
 def __getattr__(name):
     # SigScoreMethods / Signatures import torch; keep ``import fastproject_b200`` light
-    if name in ("SigScoreMethods", "Signatures", "NormalizationMethods", "synth", "distributed"):
+    if name in ("SigScoreMethods", "Signatures", "NormalizationMethods", "Interactive", "synth", "distributed"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -8,6 +8,7 @@ There is no CPU path here: a missing GPU or library raises.
 from __future__ import annotations
 
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -64,7 +65,9 @@ def to_device(arr, dtype=torch.float64):
             a = a.astype(np.float64)
         if not a.flags["C_CONTIGUOUS"]:
             a = np.ascontiguousarray(a)
-        t = torch.from_numpy(a)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)     # read-only arrays: we only read them
+            t = torch.from_numpy(a)
     t = t.to(device=dev, dtype=dtype, non_blocking=True)
     return t.contiguous()
 

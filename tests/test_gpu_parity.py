@@ -433,3 +433,36 @@ def test_normalization_midsize_bit_exact_vs_oracle_and_device_path(fp):
     want = O.calculate_sig_scores(O.ExpressionMatrix(O.row_normalization(x), w, genes, cells),
                                   [O.Signature(sig.sig_dict, False, "t", "s")], "weighted_avg", None, 5)
     assert np.array_equal(got["s"].scores, want["s"].scores)
+
+
+# ------------------------------------------------------------------ Interactive wrappers (next row N4)
+def test_interactive_dataframe_wrappers_vs_oracle(fp):
+    import pandas as pd
+    from fastproject_b200 import Interactive as I
+    c = G.load("case_synth_even")
+    genes = [str(g) for g in c["genes"]]
+    cells = [str(x) for x in c["cells"]]
+    data = pd.DataFrame(c["X"], index=genes, columns=cells)
+    weights = pd.DataFrame(c["W"], index=genes, columns=cells)
+    real = G.unpack_sigs(c, "real_", fp.S.Signature)
+    rnd = G.unpack_sigs(c, "rnd_", fp.S.Signature)
+    scores, num_genes = I.calculate_sig_scores(data, real, weights, "weighted_avg", c["Z"], int(c["min_genes"]))
+    rscores, rnum = I.calculate_sig_scores(data, rnd, weights, "weighted_avg", c["Z"], int(c["min_genes"]))
+    odata = O.ExpressionMatrix(c["X"], c["W"], genes, cells)
+    oreal = O.calculate_sig_scores(odata, G.unpack_sigs(c, "real_", O.Signature), "weighted_avg", c["Z"],
+                                   int(c["min_genes"]))
+    ornd = O.calculate_sig_scores(odata, G.unpack_sigs(c, "rnd_", O.Signature), "weighted_avg", c["Z"],
+                                  int(c["min_genes"]))
+    assert list(scores.columns) == list(oreal.keys()) and list(scores.index) == cells
+    for name in oreal:
+        assert np.array_equal(scores[name].values, oreal[name].scores)
+        assert num_genes[name] == oreal[name].numGenes
+    proj_name = sorted(G.projections(c).keys())[0]
+    coords = G.projections(c)[proj_name]
+    projection = pd.DataFrame(coords.T, index=cells, columns=["x", "y"])
+    cons, pvals, null = I.sigs_vs_projection(projection, scores, num_genes, rscores, rnum)
+    want = O.sigs_vs_projections({"proj_name": coords}, oreal, ornd)
+    assert list(cons.index) == want[0] and list(null.index) == want[5]
+    np.testing.assert_allclose(cons.values, want[2], rtol=TC_CONS_RTOL)
+    np.testing.assert_allclose(null.values, want[4], rtol=TC_CONS_RTOL)
+    np.testing.assert_allclose(pvals.values, want[3], rtol=LOGQ_RTOL, atol=1e-6)
