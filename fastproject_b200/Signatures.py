@@ -199,7 +199,8 @@ def _factor_design(values):
 
 
 def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
-                        NEIGHBORHOOD_SIZE=0.33, precision=None, sigma_per_cell=None, distributed=False):
+                        NEIGHBORHOOD_SIZE=0.33, precision=None, sigma_per_cell=None, distributed=False,
+                        prefetch_next=None):
     """Evaluates the significance of each signature vs each projection
     (Signatures.py:300-534).
 
@@ -211,6 +212,9 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
         FASTPROJECT_B200_PRECISION, else "fp64"
     :param sigma_per_cell: (extension) optional (N,) array of per-cell bandwidths
         replacing NEIGHBORHOOD_SIZE
+    :param prefetch_next: (extension) host matrices (expression, weights, ...) of the NEXT data
+        set: their upload is started on a side stream once this call has uploaded its own small
+        inputs, and overlaps the projection loop (see ``fastproject_b200.prefetch``)
     :param distributed: (extension) one process per GPU (``torch.distributed`` initialised):
         every rank passes ITS block of the signature dictionaries; the per-pair medians are
         all-gathered (the only exchange), the random background pools all ranks, and every
@@ -249,9 +253,10 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     else:
         order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
                                                     [o.numGenes for o in std_objs])
-    d_order = _engine.to_device(order, torch.int32)
-    d_gptr = _engine.to_device(gptr, torch.int32)
-    d_group = _engine.to_device(sig_group, torch.int32)
+    d_tables = _engine.to_device(np.concatenate([order, gptr, sig_group]).astype(np.int32), torch.int32)
+    d_order = d_tables[:order.size]
+    d_gptr = d_tables[order.size:order.size + gptr.size]
+    d_group = d_tables[order.size + gptr.size:]
 
     if sigma_per_cell is not None:
         sig2 = _engine.to_device(np.asarray(sigma_per_cell, dtype=np.float64) ** 2)
@@ -268,11 +273,19 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     pnum_sig_proj_matrix_p = np.zeros((len(sp_row_labels_pnum), N_PROJECTIONS))
     factor_dict = dict((s, _factor_design(sig_scores_dict[s].scores)) for s in sp_row_labels_factors)
 
-    for i, proj in enumerate(sp_col_labels):                            # :393
-        coords = _engine.to_device(np.ascontiguousarray(projections[proj], dtype=np.float64))
-        if tuple(coords.shape) != (2, N_SAMPLES):
+    for proj in sp_col_labels:
+        if tuple(np.shape(projections[proj])) != (2, N_SAMPLES):
             raise ValueError("projection %r has shape %s, expected (2, %d)"
-                             % (proj, tuple(coords.shape), N_SAMPLES))
+                             % (proj, tuple(np.shape(projections[proj])), N_SAMPLES))
+    # all projections in one upload
+    coords_all = _engine.to_device(np.stack([np.asarray(projections[p], dtype=np.float64)
+                                             for p in sp_col_labels])) if N_PROJECTIONS else None
+
+    if prefetch_next is not None:
+        _engine.prefetch(*prefetch_next)
+
+    for i, proj in enumerate(sp_col_labels):                            # :393
+        coords = coords_all[i]
         if ranks.shape[0]:
             # the rank matrix is the same for every projection: its digit planes are packed once
             _engine.consistency(coords, sig2, ranks, N_SAMPLES, out=dissim, precision=precision,

@@ -172,6 +172,12 @@ class _ExpressionCache(object):
         sample = a.reshape(-1)[idx] if a.flags["C_CONTIGUOUS"] else a.T.reshape(-1)[idx]
         return np.ascontiguousarray(sample).tobytes()
 
+    def _find(self, key, fp):
+        for i, entry in enumerate(self.entries):
+            if entry[0] == key and entry[1] == fp:
+                return i
+        return -1
+
     def get(self, a, replicated=False):
         """``replicated``: every rank of the process group holds the same host matrix (the
         expression data of a multi-GPU run); each rank then uploads 1/world of the rows over
@@ -182,21 +188,82 @@ class _ExpressionCache(object):
         if os.environ.get("FASTPROJECT_B200_NO_CACHE"):
             return upload(a)
         key, fp = self._key(a), self._fingerprint(a)
-        for i, (k, f, t) in enumerate(self.entries):
-            if k == key and f == fp:
-                self.entries.append(self.entries.pop(i))
-                return t
+        i = self._find(key, fp)
+        if i >= 0:
+            entry = self.entries.pop(i)
+            if entry[3] is not None:                 # prefetched on the copy stream: order after it
+                torch.cuda.current_stream().wait_event(entry[3])
+                entry = (entry[0], entry[1], entry[2], None)
+            self.entries.append(entry)
+            return entry[2]
         t = upload(a)
-        self.entries.append((key, fp, t))
+        self.entries.append((key, fp, t, None))
         while len(self.entries) > self.capacity:
             self.entries.pop(0)
         return t
+
+    def prefetch(self, a):
+        """Start the upload of a host matrix on a side stream and return at once; a later
+        ``get`` of the same array waits for the copy instead of issuing it.  Lets the upload of
+        the NEXT data set overlap the kernels of the current one (pinned host memory).
+
+        The host -> device copy engine serves transfers in submission order (measured: the
+        kilobyte-sized uploads of a running step -- index tables, coordinates -- waited ~90 ms
+        behind a queued 4.8 GB prefetch and stalled the compute stream; feeding the engine in
+        paced pieces from a Python thread halved the copy rate).  So issue the prefetch at a
+        point after which the running step uploads nothing more:
+        ``sigs_vs_projections(..., prefetch_next=...)`` does it right before its projection loop."""
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return
+        dev = require_cuda()
+        key, fp = self._key(a), self._fingerprint(a)
+        if self._find(key, fp) >= 0:
+            return
+        if isinstance(a, torch.Tensor):
+            host = a
+        else:
+            arr = np.asarray(a)
+            if arr.dtype == np.bool_:
+                arr = arr.astype(np.float64)
+            if not arr.flags["C_CONTIGUOUS"]:
+                arr = np.ascontiguousarray(arr)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", UserWarning)
+                host = torch.from_numpy(arr)
+        global _copy_stream
+        if _copy_stream is None:
+            _copy_stream = torch.cuda.Stream(device=dev)
+        t = torch.empty(tuple(host.shape), dtype=torch.float64, device=dev)
+        _copy_stream.wait_stream(torch.cuda.current_stream())      # the buffer may be recycled memory
+        t.record_stream(_copy_stream)
+        with torch.cuda.stream(_copy_stream):
+            t.copy_(host, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(_copy_stream)
+        self.entries.append((key, fp, t, done))
+        while len(self.entries) > self.capacity:
+            self.entries.pop(0)
+
+    def evict(self, a):
+        key, fp = self._key(a), self._fingerprint(a)
+        i = self._find(key, fp)
+        if i >= 0:
+            self.entries.pop(i)
 
     def clear(self):
         self.entries = []
 
 
+_copy_stream = None
 expression_cache = _ExpressionCache()
+
+
+def prefetch(*arrays):
+    """Public hook: start uploading host matrices (expression, weights, zero mask) that a later
+    ``calculate_sig_scores`` call will use."""
+    for a in arrays:
+        if a is not None:
+            expression_cache.prefetch(a)
 
 
 def clear_device_cache():

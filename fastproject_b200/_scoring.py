@@ -189,8 +189,10 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
         z = _engine.expression_cache.get(zero_locations, replicated)
     kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
         signatures, data.row_labels, min_signature_genes, raise_on_reject)
-    d_ptr = _engine.to_device(sig_ptr, torch.int32)
-    d_gene = _engine.to_device(sig_gene, torch.int32)
+    # one upload for the two int32 tables (few, larger host -> device transfers: they share the
+    # copy engine with a prefetch of the next data set)
+    d_tables = _engine.to_device(np.concatenate([sig_ptr, sig_gene]), torch.int32)
+    d_ptr, d_gene = d_tables[:sig_ptr.size], d_tables[sig_ptr.size:]
     d_sign = _engine.to_device(sig_sign, torch.int8)
     scores = _engine.score_signatures(method, x, w, z, d_ptr, d_gene, d_sign, len(kept))
     batch = ScoreBatch(scores, n_cells, counts)
