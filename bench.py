@@ -352,7 +352,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     # step uploads its own inputs; at one GPU the upload of step k+1 is started inside step k's
     # sigs_vs_projections(prefetch_next=...) and overlaps its projection loop
     host = []
-    for _ in range(2 if world == 1 else 1):
+    for _ in range(2):
         xh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
         wh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
         xh.copy_(wl["x"]); wh.copy_(wl["w"])
@@ -360,7 +360,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     torch.cuda.synchronize()
     # a pipeline needs a few steps to show its steady state; the first timed step still uploads
     # its matrices synchronously
-    steps = max(args.steps, 6) if world == 1 else max(1, min(args.steps, 3))
+    steps = max(args.steps, 6)
     d2h = 0
 
     def one_step(data, nxt):
@@ -387,8 +387,10 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     t0 = time.perf_counter()
     for it in range(steps):
         data = host[it % len(host)]
-        nxt = host[(it + 1) % len(host)] if (world == 1 and it + 1 < steps) else None
+        nxt = host[(it + 1) % len(host)] if it + 1 < steps else None
         real, rnd, d2h = one_step(data, nxt)
+        if os.environ.get("FP_BENCH_DEBUG"):
+            sys.stderr.write("e2e step %d done at %.1f ms\n" % (it, 1e3 * (time.perf_counter() - t0)))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -405,10 +407,11 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     return {"value": world * n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h) * world, "s_per_step": t, "steps": len(times),
             "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections(distributed=%s), "
-                   "pinned host inputs; %s" % (world > 1, "the expression matrices are uploaded once per job "
-                   "(row shards over every rank's PCIe link + NCCL all-gather)" if world > 1 else
-                   "steps back to back, the upload of the next step's matrices (prefetch_next=) "
-                   "overlaps the projection loop of the current one")}
+                   "pinned host inputs; steps back to back, the upload of the next step's matrices "
+                   "(prefetch_next=) overlaps the projection loop of the current one%s"
+                   % (world > 1, "; the expression matrices are one data set per job: every rank uploads "
+                      "1/world of the rows over its PCIe link and the rows are all-gathered over NVLink"
+                      if world > 1 else "")}
 
 
 # ----------------------------------------------------------------------------

@@ -282,7 +282,7 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
                                              for p in sp_col_labels])) if N_PROJECTIONS else None
 
     if prefetch_next is not None:
-        _engine.prefetch(*prefetch_next)
+        _engine.prefetch(*prefetch_next, replicated=distributed)
 
     for i, proj in enumerate(sp_col_labels):                            # :393
         coords = coords_all[i]

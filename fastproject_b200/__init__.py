@@ -15,12 +15,12 @@ __version__ = "0.1.0"
 __all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Interactive", "Global", "synth"]
 
 
-def prefetch(*arrays):
+def prefetch(*arrays, **kw):
     """Start the host -> device upload of expression / weight / zero-mask matrices on a side
     stream; ``Signatures.calculate_sig_scores`` on the same arrays then finds them resident.
     Overlaps the upload of the next data set with the kernels of the current one."""
     from . import _engine
-    _engine.prefetch(*arrays)
+    _engine.prefetch(*arrays, **kw)
 
 
 def __getattr__(name):

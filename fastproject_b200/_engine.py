@@ -202,7 +202,7 @@ class _ExpressionCache(object):
             self.entries.pop(0)
         return t
 
-    def prefetch(self, a):
+    def prefetch(self, a, replicated=False):
         """Start the upload of a host matrix on a side stream and return at once; a later
         ``get`` of the same array waits for the copy instead of issuing it.  Lets the upload of
         the NEXT data set overlap the kernels of the current one (pinned host memory).
@@ -233,13 +233,18 @@ class _ExpressionCache(object):
         global _copy_stream
         if _copy_stream is None:
             _copy_stream = torch.cuda.Stream(device=dev)
-        t = torch.empty(tuple(host.shape), dtype=torch.float64, device=dev)
         _copy_stream.wait_stream(torch.cuda.current_stream())      # the buffer may be recycled memory
-        t.record_stream(_copy_stream)
         with torch.cuda.stream(_copy_stream):
-            t.copy_(host, non_blocking=True)
+            if replicated:
+                # row shard over this rank's PCIe link + NCCL all-gather, all on the copy stream;
+                # every rank issues its collectives in the same program order
+                t = to_device_replicated(host)
+            else:
+                t = torch.empty(tuple(host.shape), dtype=torch.float64, device=dev)
+                t.copy_(host, non_blocking=True)
             done = torch.cuda.Event()
             done.record(_copy_stream)
+        t.record_stream(torch.cuda.current_stream())
         self.entries.append((key, fp, t, done))
         while len(self.entries) > self.capacity:
             self.entries.pop(0)
@@ -258,12 +263,13 @@ _copy_stream = None
 expression_cache = _ExpressionCache()
 
 
-def prefetch(*arrays):
+def prefetch(*arrays, **kw):
     """Public hook: start uploading host matrices (expression, weights, zero mask) that a later
-    ``calculate_sig_scores`` call will use."""
+    ``calculate_sig_scores`` call will use.  ``replicated=True``: the cooperative multi-GPU
+    upload (same arrays on every rank; every rank must make the same call)."""
     for a in arrays:
         if a is not None:
-            expression_cache.prefetch(a)
+            expression_cache.prefetch(a, kw.get("replicated", False))
 
 
 def clear_device_cache():
