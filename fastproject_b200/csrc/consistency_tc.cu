@@ -502,8 +502,8 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
                     pk[a][2 * h + 1] = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
                 }
             }
-            if (dbg & 128) mbar_spin(&empty[s], ph ^ 1); else
-            mbar_wait(&empty[s], ph ^ 1);
+            if (dbg & 128) mbar_spin(&empty[s], ph ^ 1);
+            else mbar_wait(&empty[s], ph ^ 1);
             uint8_t *bst = smem + s * L::stage_bytes + SR * A_PLANE_BYTES;
 #pragma unroll
             for (int a = 0; a < WD; ++a)
