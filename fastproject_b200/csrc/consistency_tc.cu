@@ -18,12 +18,15 @@
 //     cores of the CTA that consumes it and written straight into shared
 //     memory as four unsigned 8-bit digit planes (the UMMA B operand);
 //   * the values are half-integers (average ranks, one-hot / binary columns), so
-//     r_j = 2 v_j - (N + 1) is an integer; it is cut into balanced signed base-256
-//     digits (planes of s8, the UMMA A operand, loaded by TMA, 128-byte swizzle);
-//   * every (weight digit, value digit) plane pair is one MMA; pairs of equal
-//     weight 256^(4-c) share an s32 accumulator ("class" c); sum_j W_ij r_j is
-//     rebuilt exactly in int64 in the epilogue.  The lowest class (2^-32 relative,
-//     below the weight quantisation) is not computed;
+//     r_j = (2 v_j - centre) * 2^shift is an integer (centre and shift from the value
+//     range: N + 1 for ranks; the top digit is always well used); it is cut into two
+//     (N <= 32 640) or three balanced signed base-256 digits (planes of s8, the UMMA A
+//     operand, loaded by TMA, 128-byte swizzle);
+//   * every (weight digit a, value digit b) plane pair with a + b <= 3 is one MMA;
+//     pairs of equal weight share an s32 accumulator ("class" a + b); sum_j W_ij r_j
+//     is rebuilt exactly in int64 in the epilogue.  The classes below 2^-32 of the top
+//     one (below the weight quantisation) are not computed; with three digits the
+//     accumulators are drained every 16 384 cells j so that they cannot overflow;
 //   * the normaliser sum_j W_ij comes from the same MMAs through a row of ones
 //     appended to every block of 127 signatures, so numerator and denominator
 //     use identical quantised weights (the quotient is an exact weighted mean
@@ -58,7 +61,8 @@ constexpr int A_PLANE_BYTES = TM * KS;    // 16 KB: one value digit plane, one s
 constexpr int B_PLANE_BYTES = TNH * KS;   //  8 KB: one weight digit plane of this CTA's 64 cells
 constexpr int NCLASS = 4;
 constexpr int TAB = 128;           // 2^(k/128) table ...
-constexpr int TAB_COPIES = 16;     // ... one copy per lane of a half-warp: LDS.64 without bank conflicts
+constexpr int TAB_COPIES = 16;     // ... 16 interleaved copies (lanes l and l+16 share one; 32 copies of a
+                                   // 64-entry table were measured: no faster)
 // s32 accumulators: a class sums at most 3 digit products of magnitude <= 255 * 128 per j
 constexpr int CHUNK_STAGES_3 = 128;       // three value digits: drain every 16 384 cells j
 
