@@ -4,16 +4,31 @@
 // (/root/reference/FastProject/SigScoreMethods.py:170-178) for all K signatures
 // at once, and the rank-matrix assembly of Signatures.py:359-369.
 //
-// Step 1: segmented LSD radix sort of (score, cell) pairs, one segment per
-//         signature row (CUB device primitive -- a library call; this step is
-//         sort-bound and far below the contraction in cost).
-// Step 2: our kernel turns sorted positions into 1-based average ranks:
-//         a key without an equal neighbour gets position+1; members of a tie
-//         run [a,b) all get (a + b + 1) / 2, the run being found by two binary
-//         searches on the sorted row (no serial walk, so a constant row costs
-//         the same as any other).  Comparisons are on double values, so -0.0
-//         ties with +0.0 exactly as in rankdata.  A row holding a NaN yields
-//         NaN everywhere (scipy nan_policy="propagate").
+// A full sort of the 64-bit scores is not needed to rank them: a monotone
+// SHORT key puts every cell within a few positions of its final place, and the
+// few cells that share a short key are ordered by looking at their doubles.
+//
+// Step 1 (quantise_rows_kernel): per row, min / max / NaN scan, then the key
+//         q = trunc((v - min) * (2^bits - 1) / (max - min)), bits ~ log2(N) + 3
+//         rounded up to whole radix digits.  Every operation is monotone in v,
+//         so v < u implies q(v) <= q(u) whatever the rounding.
+// Step 2: segmented LSD radix sort of (q, cell) pairs over `bits` bits only
+//         (CUB device primitive -- a library call; 3 passes over 8-byte pairs
+//         for 20 000 cells instead of 11 passes over 12-byte pairs for the
+//         doubles).
+// Step 3 (assign_ranks_kernel): a cell alone in its key bin has rank
+//         position + 1.  Cells sharing a bin [a, b) count the bin's doubles
+//         below and equal to their own: rank = a + less + (equal + 1) / 2
+//         ("average") or a + less + 1 ("min").  Comparisons are on double
+//         values, so -0.0 ties with +0.0 exactly as in rankdata.
+// Step 4 (long_bins_*_kernel): bins longer than kShortBin cells (a constant
+//         row, the zeros of an expression column, data squeezed by an outlier)
+//         go to a device work list, one warp each: an all-equal bin is ranked
+//         in O(L); a mixed one by counting against the whole bin (large mixed
+//         bins by a whole CTA).  No host round trip decides between the paths.
+// A row holding a NaN yields NaN everywhere (scipy nan_policy="propagate").
+// Rows with infinities fall back to keys cut from the order-preserving bit
+// pattern of the double (coarse, hence slower through step 4, but exact).
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -23,6 +38,9 @@
 namespace {
 
 constexpr long kMaxBatchElems = 1L << 27;  // elements sorted per CUB call
+constexpr int kShortBin = 32;              // bins up to this size are counted in place
+constexpr int kWarpBin = 1024;             // mixed bins up to this size are counted by one warp
+constexpr int kRadixBits = 6;              // digit width of CUB's segmented sort passes
 
 struct RowBegin {
     long ld;
@@ -37,56 +55,228 @@ using CountIt = thrust::counting_iterator<long>;
 using BeginIt = thrust::transform_iterator<RowBegin, CountIt, long>;
 using EndIt = thrust::transform_iterator<RowEnd, CountIt, long>;
 
-__global__ void fill_cell_index_kernel(int32_t *__restrict__ idx, long rows, long N, long ld) {
-    const long total = rows * ld;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long)gridDim.x * blockDim.x) {
-        const long c = i % ld;
-        idx[i] = (int32_t)(c < N ? c : 0);
+struct LongBin {
+    int row, a, b, pad;
+};
+
+// order-preserving bit pattern of a double (-0.0 folded onto +0.0 first)
+__device__ __forceinline__ uint64_t ordered_bits(double v) {
+    const uint64_t u = (uint64_t)__double_as_longlong(v + 0.0);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+constexpr int QUANT_THREADS = 512;
+
+// one CTA per row: range scan, then keys (second read of the row comes from L2)
+__global__ void __launch_bounds__(QUANT_THREADS)
+quantise_rows_kernel(const double *__restrict__ scores, long rows, long N, long ld, int bits,
+                     uint32_t *__restrict__ keys, int32_t *__restrict__ cells, int32_t *__restrict__ row_nan) {
+    __shared__ double s_min[QUANT_THREADS / 32], s_max[QUANT_THREADS / 32];
+    __shared__ int s_flag[QUANT_THREADS / 32];
+    __shared__ double s_lo, s_scale;
+    __shared__ int s_mode;                                   // 0 linear keys, 1 bit-pattern keys, 2 NaN row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double top = (double)((1ULL << bits) - 1);
+    for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const double *src = scores + row * ld;
+        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
+        int flag = 0;                                        // bit 0: NaN seen, bit 1: infinity seen
+        for (long c = threadIdx.x; c < N; c += QUANT_THREADS) {
+            const double v = src[c];
+            if (v != v) flag |= 1;
+            else {
+                if (isinf(v)) flag |= 2;
+                mn = fmin(mn, v);
+                mx = fmax(mx, v);
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+        }
+        if (lane == 0) { s_min[warp] = mn; s_max[warp] = mx; s_flag[warp] = flag; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < QUANT_THREADS / 32; ++w) {
+                mn = fmin(mn, s_min[w]);
+                mx = fmax(mx, s_max[w]);
+                flag |= s_flag[w];
+            }
+            const double span = mx - mn;                     // may overflow to +inf: scale 0, one bin
+            s_lo = mn;
+            const double scale = (span > 0.0 && !isinf(span)) ? top / span : 0.0;
+            s_scale = scale;                                 // a denormal span overflows it: bit-pattern keys
+            s_mode = (flag & 1) ? 2 : ((flag & 2) || isinf(span) || isinf(scale)) ? 1 : 0;
+            row_nan[row] = (flag & 1);
+        }
+        __syncthreads();
+        const double lo = s_lo, scale = s_scale;
+        const int mode = s_mode;
+        uint32_t *kd = keys + row * ld;
+        int32_t *cd = cells + row * ld;
+        for (long c = threadIdx.x; c < ld; c += QUANT_THREADS) {
+            uint32_t q = 0;
+            if (c < N && mode != 2) {
+                const double v = src[c];
+                if (mode == 0) {
+                    const double t = fmin((v - lo) * scale, top);
+                    q = (uint32_t)__double2ull_rz(t);
+                } else {
+                    q = (uint32_t)(ordered_bits(v) >> (64 - bits));
+                }
+            }
+            kd[c] = q;
+            cd[c] = (int32_t)(c < N ? c : 0);
+        }
+        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(256)
-assign_average_ranks_kernel(const double *__restrict__ sorted_keys,
-                            const int32_t *__restrict__ sorted_cell, long rows, long N, long ld,
-                            double *__restrict__ out_ranks, long ld_out, int method) {
+assign_ranks_kernel(const double *__restrict__ scores, const uint32_t *__restrict__ sorted_keys,
+                    const int32_t *__restrict__ sorted_cell, const int32_t *__restrict__ row_nan, long rows, long N,
+                    long ld, double *__restrict__ out_ranks, long ld_out, int method, LongBin *__restrict__ work,
+                    unsigned *__restrict__ work_count, long row0) {
   for (long row = blockIdx.y; row < rows; row += gridDim.y) {
-    const double *ks = sorted_keys + row * ld;
+    const uint32_t *ks = sorted_keys + row * ld;
     const int32_t *cs = sorted_cell + row * ld;
+    const double *src = scores + row * ld;
     double *out = out_ranks + row * ld_out;
-    const double first = ks[0], last = ks[N - 1];
-    const bool has_nan = (first != first) || (last != last);
+    const bool has_nan = row_nan[row] != 0;
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < N;
          p += (long)gridDim.x * blockDim.x) {
-        const double v = ks[p];
-        double rank;
+        const int32_t cell = cs[p];
         if (has_nan) {
-            rank = __longlong_as_double(0x7ff8000000000000LL);
-        } else {
-            const bool tie_left = p > 0 && ks[p - 1] == v;
-            const bool tie_right = p + 1 < N && ks[p + 1] == v;
-            if (!tie_left && !tie_right) {
-                rank = (double)(p + 1);
-            } else {
-                long lo = 0, hi = p;                 // first index with ks[idx] == v
+            out[cell] = __longlong_as_double(0x7ff8000000000000LL);
+            continue;
+        }
+        const uint32_t k = ks[p];
+        const bool tie_left = p > 0 && ks[p - 1] == k;
+        const bool tie_right = p + 1 < N && ks[p + 1] == k;
+        if (!tie_left && !tie_right) {
+            out[cell] = (double)(p + 1);
+            continue;
+        }
+        long a = p, b = p + 1;                       // the bin [a, b): a short walk, then bisection
+        {
+            int steps = 0;
+            while (a > 0 && ks[a - 1] == k && steps < kShortBin) { --a; ++steps; }
+            if (a > 0 && ks[a - 1] == k) {
+                long lo = 0, hi = a;                 // first index with ks[idx] == k
                 while (lo < hi) {
                     const long mid = (lo + hi) >> 1;
-                    if (ks[mid] < v) lo = mid + 1; else hi = mid;
+                    if (ks[mid] < k) lo = mid + 1; else hi = mid;
                 }
-                const long a = lo;
-                lo = p + 1; hi = N;                  // first index with ks[idx] > v
+                a = lo;
+            }
+            steps = 0;
+            while (b < N && ks[b] == k && steps < kShortBin) { ++b; ++steps; }
+            if (b < N && ks[b] == k) {
+                long lo = b, hi = N;                 // first index with ks[idx] > k
                 while (lo < hi) {
                     const long mid = (lo + hi) >> 1;
-                    if (ks[mid] > v) hi = mid; else lo = mid + 1;
+                    if (ks[mid] > k) hi = mid; else lo = mid + 1;
                 }
-                const long b = lo;
-                // "average": mean of ranks a+1 .. b (exact); "min": the smallest of them
-                rank = method == FP_RANK_MIN ? (double)(a + 1) : 0.5 * (double)(a + b + 1);
+                b = lo;
             }
         }
-        out[cs[p]] = rank;
+        if (b - a > kShortBin) {
+            if (p == a) {
+                const unsigned slot = atomicAdd(work_count, 1u);
+                work[slot] = LongBin{(int)(row0 + row), (int)a, (int)b, 0};
+            }
+            continue;
+        }
+        const double v = src[cell];
+        int less = 0, equal = 0;
+        for (long q = a; q < b; ++q) {
+            const double u = src[cs[q]];
+            less += u < v;
+            equal += u == v;
+        }
+        // "average": mean of ranks a+less+1 .. a+less+equal (exact); "min": the smallest of them
+        out[cell] = method == FP_RANK_MIN ? (double)(a + less + 1) : (double)(a + less) + 0.5 * (double)(equal + 1);
     }
   }
+}
+
+// One WARP per listed bin.  `scores`, `sorted_cell`, `out_ranks` are the batch bases and
+// LongBin::row is batch-relative.  An all-equal bin is one tie run; a mixed bin of up to
+// kWarpBin cells is counted by the warp; larger mixed bins move on to the CTA-wide kernel.
+__global__ void __launch_bounds__(256)
+long_bins_warp_kernel(const double *__restrict__ scores, const int32_t *__restrict__ sorted_cell, long ld,
+                      double *__restrict__ out_ranks, long ld_out, int method, const LongBin *__restrict__ work,
+                      const unsigned *__restrict__ work_count, LongBin *__restrict__ big,
+                      unsigned *__restrict__ big_count) {
+    const unsigned n_work = *work_count;
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_work; e += warps) {
+        const LongBin w = work[e];
+        const double *src = scores + (long)w.row * ld;
+        const int32_t *cs = sorted_cell + (long)w.row * ld;
+        double *out = out_ranks + (long)w.row * ld_out;
+        const long a = w.a, L = w.b - w.a;
+        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
+        for (long i = lane; i < L; i += 32) {
+            const double v = src[cs[a + i]];
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+        for (int o = 16; o; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mn == mx) {
+            const double r = method == FP_RANK_MIN ? (double)(a + 1) : (double)a + 0.5 * (double)(L + 1);
+            for (long i = lane; i < L; i += 32) out[cs[a + i]] = r;
+            continue;
+        }
+        if (L > kWarpBin) {
+            if (lane == 0) big[atomicAdd(big_count, 1u)] = w;
+            continue;
+        }
+        for (long i = lane; i < L; i += 32) {
+            const int32_t cell = cs[a + i];
+            const double v = src[cell];
+            int less = 0, equal = 0;
+            for (long q = 0; q < L; ++q) {            // the whole warp reads the same address
+                const double u = src[cs[a + q]];
+                less += u < v;
+                equal += u == v;
+            }
+            out[cell] = method == FP_RANK_MIN ? (double)(a + less + 1)
+                                              : (double)(a + less) + 0.5 * (double)(equal + 1);
+        }
+    }
+}
+
+// one CTA per large mixed bin: every cell counts against the whole bin
+__global__ void __launch_bounds__(256)
+long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restrict__ sorted_cell, long ld,
+                     double *__restrict__ out_ranks, long ld_out, int method, const LongBin *__restrict__ big,
+                     const unsigned *__restrict__ big_count) {
+    const unsigned n_big = *big_count;
+    for (unsigned e = blockIdx.x; e < n_big; e += gridDim.x) {
+        const LongBin w = big[e];
+        const double *src = scores + (long)w.row * ld;
+        const int32_t *cs = sorted_cell + (long)w.row * ld;
+        double *out = out_ranks + (long)w.row * ld_out;
+        const long a = w.a, L = w.b - w.a;
+        for (long i = threadIdx.x; i < L; i += blockDim.x) {
+            const int32_t cell = cs[a + i];
+            const double v = src[cell];
+            long less = 0, equal = 0;
+            for (long q = 0; q < L; ++q) {
+                const double u = src[cs[a + q]];
+                less += u < v;
+                equal += u == v;
+            }
+            out[cell] = method == FP_RANK_MIN ? (double)(a + less + 1)
+                                              : (double)(a + less) + 0.5 * (double)(equal + 1);
+        }
+    }
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -98,26 +288,50 @@ long batch_rows(long K, long ld) {
     return b;
 }
 
+// key width: ~8 empty bins per cell, in whole radix digits
+int key_bits(long N) {
+    int lg = 0;
+    while ((1L << lg) < N) ++lg;
+    int bits = (lg + 3 + kRadixBits - 1) / kRadixBits * kRadixBits;
+    if (bits < 2 * kRadixBits) bits = 2 * kRadixBits;
+    if (bits > 30) bits = 30;
+    return bits;
+}
+
 size_t cub_temp_bytes(long rows, long N, long ld) {
     size_t bytes = 0;
     CountIt cnt(0);
     BeginIt beg(cnt, RowBegin{ld});
     EndIt end(cnt, RowEnd{ld, N});
-    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, bytes, (const double *)nullptr,
-                                             (double *)nullptr, (const int32_t *)nullptr,
+    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr,
+                                             (uint32_t *)nullptr, (const int32_t *)nullptr,
                                              (int32_t *)nullptr, (int)(rows * ld), (int)rows, beg,
-                                             end, 0, 64, (cudaStream_t)0);
+                                             end, 0, key_bits(N), (cudaStream_t)0);
     return bytes;
+}
+
+struct Layout {
+    size_t idx_b, nan_b, work_b, temp_b, total;
+};
+
+Layout layout(long rows, long N, long ld) {
+    Layout l;
+    l.idx_b = align_up((size_t)rows * ld * 4);
+    l.nan_b = align_up((size_t)rows * 4);
+    // at most one entry per kShortBin + 1 cells, plus the counter
+    l.work_b = align_up(((size_t)rows * ld / (kShortBin + 1) + 1) * sizeof(LongBin) + 256) +
+               align_up(((size_t)rows * ld / (kWarpBin + 1) + 1) * sizeof(LongBin));
+    l.temp_b = align_up(cub_temp_bytes(rows, N, ld));
+    l.total = 4 * l.idx_b + l.nan_b + l.work_b + l.temp_b;
+    return l;
 }
 
 }  // namespace
 
 extern "C" size_t fp_rank_workspace_bytes(int64_t K, int64_t N, int64_t ld) {
     if (K <= 0 || N <= 0 || ld < N) return 0;
-    const long rows = batch_rows(K, ld);
-    // parts: sorted keys, cell index in, cell index out, CUB temp
-    return align_up((size_t)rows * ld * 8) + 2 * align_up((size_t)rows * ld * 4) +
-           align_up(cub_temp_bytes(rows, N, ld)) + 1024;
+    // parts: keys in / out, cell index in / out, NaN flags, long-bin work list, CUB temp
+    return layout(batch_rows(K, ld), N, ld).total + 1024;
 }
 
 extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld, double *out_ranks,
@@ -139,39 +353,55 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
     FP_CHECK_ARG(N < (1L << 31), "fp_rank_columns: N too large");
     if (K == 0) return FP_OK;
     const long rows = batch_rows(K, ld);
-    const size_t keys_b = align_up((size_t)rows * ld * 8), idx_b = align_up((size_t)rows * ld * 4);
-    const size_t temp_b = cub_temp_bytes(rows, N, ld);
-    if (!workspace || workspace_bytes < keys_b + 2 * idx_b + align_up(temp_b)) {
-        fp::set_error("fp_rank_columns: workspace %zu bytes < required %zu", workspace_bytes,
-                      keys_b + 2 * idx_b + align_up(temp_b));
+    const Layout l = layout(rows, N, ld);
+    if (!workspace || workspace_bytes < l.total) {
+        fp::set_error("fp_rank_columns: workspace %zu bytes < required %zu", workspace_bytes, l.total);
         return FP_EWORKSPACE;
     }
     char *ws = static_cast<char *>(workspace);
-    double *keys_sorted = reinterpret_cast<double *>(ws);
-    int32_t *cell_in = reinterpret_cast<int32_t *>(ws + keys_b);
-    int32_t *cell_sorted = reinterpret_cast<int32_t *>(ws + keys_b + idx_b);
-    void *cub_temp = ws + keys_b + 2 * idx_b;
+    uint32_t *keys_in = reinterpret_cast<uint32_t *>(ws);
+    uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(ws + l.idx_b);
+    int32_t *cell_in = reinterpret_cast<int32_t *>(ws + 2 * l.idx_b);
+    int32_t *cell_sorted = reinterpret_cast<int32_t *>(ws + 3 * l.idx_b);
+    int32_t *row_nan = reinterpret_cast<int32_t *>(ws + 4 * l.idx_b);
+    unsigned *work_count = reinterpret_cast<unsigned *>(ws + 4 * l.idx_b + l.nan_b);
+    LongBin *work = reinterpret_cast<LongBin *>(ws + 4 * l.idx_b + l.nan_b + 256);
+    LongBin *big = reinterpret_cast<LongBin *>(
+        ws + 4 * l.idx_b + l.nan_b + align_up(((size_t)rows * ld / (kShortBin + 1) + 1) * sizeof(LongBin) + 256));
+    unsigned *big_count = work_count + 1;
+    void *cub_temp = ws + 4 * l.idx_b + l.nan_b + l.work_b;
     cudaStream_t st = fp::as_stream(stream);
-
-    fill_cell_index_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(cell_in, rows, N, ld);
-    FP_CHECK_LAUNCH("fill_cell_index_kernel");
+    const int bits = key_bits(N);
 
     for (long k0 = 0; k0 < K; k0 += rows) {
         const long nb = (K - k0 < rows) ? (K - k0) : rows;
+        const double *src = scores + k0 * ld;
+        double *dst = out_ranks + k0 * ld;
+        FP_CHECK_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(unsigned), st));
+        const long cap = (long)fp::sm_count() * 4;
+        quantise_rows_kernel<<<(unsigned)(nb < cap ? nb : cap), QUANT_THREADS, 0, st>>>(src, nb, N, ld, bits, keys_in,
+                                                                                       cell_in, row_nan);
+        FP_CHECK_LAUNCH("quantise_rows_kernel");
         CountIt cnt(0);
         BeginIt beg(cnt, RowBegin{ld});
         EndIt end(cnt, RowEnd{ld, N});
-        size_t tb = temp_b;
+        size_t tb = l.temp_b;
         FP_CHECK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(
-            cub_temp, tb, scores + k0 * ld, keys_sorted, cell_in, cell_sorted, (int)(nb * ld),
-            (int)nb, beg, end, 0, 64, st));
-        fp::count_launch(8);  // library launches (one per radix pass), counted approximately
+            cub_temp, tb, keys_in, keys_sorted, cell_in, cell_sorted, (int)(nb * ld), (int)nb, beg, end, 0, bits,
+            st));
+        fp::count_launch(bits / kRadixBits);  // library launches, one per radix pass
         unsigned gx = (unsigned)((N + 255) / 256);
         if (gx > 64) gx = 64;
         const unsigned gy = (unsigned)(nb < 32768 ? nb : 32768);
-        assign_average_ranks_kernel<<<dim3(gx, gy), 256, 0, st>>>(
-            keys_sorted, cell_sorted, nb, N, ld, out_ranks + k0 * ld, ld, method);
-        FP_CHECK_LAUNCH("assign_average_ranks_kernel");
+        assign_ranks_kernel<<<dim3(gx, gy), 256, 0, st>>>(src, keys_sorted, cell_sorted, row_nan, nb, N, ld, dst, ld,
+                                                          method, work, work_count, 0);
+        FP_CHECK_LAUNCH("assign_ranks_kernel");
+        long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
+                                                                  work_count, big, big_count);
+        FP_CHECK_LAUNCH("long_bins_warp_kernel");
+        long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, big,
+                                                                 big_count);
+        FP_CHECK_LAUNCH("long_bins_cta_kernel");
     }
     return FP_OK;
 }

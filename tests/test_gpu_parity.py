@@ -136,6 +136,46 @@ def test_rank_ties_constant_negative_zero_and_nan(fp):
         fp.M.SignatureScores(["a"], "f", [], True, True, 0).ranks
 
 
+def test_rank_short_keys_hard_cases(fp):
+    """The rank path sorts a short monotone key and orders the cells sharing a key bin by their
+    doubles: exercise every bin regime against scipy (bit-exact), both tie rules."""
+    import torch
+    from scipy.stats import rankdata
+    from fastproject_b200 import _engine as E, _native
+    rng = np.random.RandomState(3)
+    n = 5000
+    rows = [
+        1.0 + np.arange(n) * 1e-13,                                    # distinct doubles, one outlier below:
+        rng.permutation(1.0 + np.arange(n) * 1e-13),                   # ... everything in a few key bins
+        np.r_[rng.permutation(np.repeat(rng.normal(size=40), 100)), rng.normal(size=n - 4000)],  # long tie runs
+        np.r_[np.inf, -np.inf, rng.normal(size=n - 2)],                # infinities -> bit-pattern keys
+        np.r_[np.inf, np.inf, -np.inf, np.zeros(n - 3)],
+        rng.normal(size=n) * 1e-320,                                   # denormals
+        np.r_[1e308, -1e308, rng.normal(size=n - 2)],                  # span overflows
+        np.where(rng.rand(n) < 0.6, 0.0, rng.gamma(1.0, size=n)),      # expression-like: a zero bin + a tail
+        np.zeros(n),
+        rng.randint(0, 2, size=n).astype(float),
+        np.r_[np.nan, rng.normal(size=n - 1)],
+    ]
+    rows[0][0] = -1e6
+    rows[1][7] = 1e9
+    x = np.ascontiguousarray(np.array(rows))
+    dev = torch.as_tensor(x).cuda()
+    for method, name in ((_native.RANK_AVERAGE, "average"), (_native.RANK_MIN, "min")):
+        got = E.rank_rows(dev, n, method).cpu().numpy()
+        for i, v in enumerate(rows):
+            if np.isnan(v).any():
+                assert np.isnan(got[i]).all()
+            else:
+                assert np.array_equal(got[i], rankdata(v, method=name)), (i, name)
+    # padded leading dimension and many rows
+    k, ld = 300, 1056
+    y = rng.normal(size=(k, ld)); y[::7, :1001] = np.round(y[::7, :1001], 1)
+    got = E.rank_rows(torch.as_tensor(y).cuda(), 1001).cpu().numpy()
+    for i in range(k):
+        assert np.array_equal(got[i, :1001], rankdata(y[i, :1001]))
+
+
 # ------------------------------------------------------------------ kernels through the engine
 @pytest.mark.parametrize("n", [1, 2, 7, 64, 65, 1000, 4097])
 def test_row_medians_exact(fp, n):
