@@ -602,6 +602,266 @@ consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const Cel
     if (warp == 0) tmem_dealloc_pair(tmem, 512);
 }
 
+// ===========================================================================
+// Two-kernel form: the weight digit planes of a SLAB of cells i (all j) are generated once
+// into HBM / L2 and every block of signatures streams them by TMA, instead of every pair of
+// signature blocks regenerating them (14 times at 3 500 signatures).
+// ===========================================================================
+constexpr int WG_THREADS = 256;
+constexpr int WG_COLS = 8;                 // cells j per thread: one 8-byte store per digit plane
+constexpr int WG_ROWS = 32;                // cells i per CTA
+
+// planes[a][i - i_first][j] = digit a (0 = most significant) of W_ij; rows of Npad bytes
+__global__ void __launch_bounds__(WG_THREADS)
+weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj, long i_first, long slab_rows,
+                     long plane_rows, long Npad, uint8_t *__restrict__ planes) {
+    __shared__ __align__(16) double tab[TAB * TAB_COPIES];
+    __shared__ CellI rows_s[WG_ROWS];
+    for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += WG_THREADS)
+        tab[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
+    const long r0 = (long)blockIdx.y * WG_ROWS;                   // slab-relative first row
+    if (threadIdx.x < WG_ROWS) rows_s[threadIdx.x] = ci[i_first + r0 + threadIdx.x];
+    __syncthreads();
+    const long j0 = ((long)blockIdx.x * WG_THREADS + threadIdx.x) * WG_COLS;
+    if (j0 >= Npad) return;
+    const char *my_tab = reinterpret_cast<const char *>(tab + (threadIdx.x & (TAB_COPIES - 1)));
+    double jx[WG_COLS], jy[WG_COLS], jn[WG_COLS];
+#pragma unroll
+    for (int e = 0; e < WG_COLS; ++e) {
+        const CellJ r = cj[j0 + e];
+        jx[e] = r.x;
+        jy[e] = r.y;
+        jn[e] = r.nb;
+    }
+    const long rows = min((long)WG_ROWS, slab_rows - r0);
+#pragma unroll 1
+    for (long r = 0; r < rows; ++r) {
+        const CellI me = rows_s[r];
+        uint32_t w[WG_COLS];
+#pragma unroll
+        for (int e = 0; e < WG_COLS; ++e) {
+            double t = fma(me.c, jn[e], me.alpha);
+            t = fma(me.x2c, jx[e], t);
+            t = fma(me.y2c, jy[e], t);
+            w[e] = weight_fixed32(t, my_tab);
+        }
+        // weights[diag] = 0 (Signatures.py:399)
+        const long dj = i_first + r0 + r - j0;
+        if (dj >= 0 && dj < WG_COLS) {
+#pragma unroll
+            for (int e = 0; e < WG_COLS; ++e)
+                if (e == dj) w[e] = 0;
+        }
+#pragma unroll
+        for (int a = 0; a < WD; ++a) {
+            const uint32_t sel = (3 - a) * 0x11 + 0x40;           // byte (3-a) of x, byte (3-a) of y
+            uint2 v;
+            v.x = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+            v.y = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
+            *reinterpret_cast<uint2 *>(planes + ((long)a * plane_rows + r0 + r) * Npad + j0) = v;
+        }
+    }
+}
+
+template <int SR>
+struct MmaSmem {
+    static constexpr int stages = SR == 2 ? 3 : 2;
+    static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
+    static constexpr int den_off = stages * stage_bytes;
+    static constexpr int bar_off = den_off + TN * 8;
+    static constexpr int total = bar_off + 256;
+};
+
+// Pair of CTAs: 2 x 127 signatures (+ ones rows) x 128 cells i (tile blockIdx.y of the slab);
+// value planes (A) and weight planes (B) both arrive by TMA.  blockIdx.x = signature-block pair
+// * 2 + CTA rank: pairs that run together share the cell tile, so its weight planes are read
+// from HBM once and from L2 by the other signature blocks.
+template <int SR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __grid_constant__ CUtensorMap tmap_weights,
+                       const double *__restrict__ values, long ld, double *__restrict__ out, long ld_out, long N,
+                       long K, long Kpad, long i_first, long plane_rows, int n_stages, int chunk_stages,
+                       int output_kind, const unsigned long long *__restrict__ range, const int *__restrict__ flag,
+                       int dbg) {
+    using L = MmaSmem<SR>;
+    constexpr int STAGES = L::stages;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    double *den_s = reinterpret_cast<double *>(smem + L::den_off);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES] leader's are used
+    uint64_t *empty = full + 4;                                                  // [STAGES] one per CTA
+    uint64_t *accum_full = empty + 4;                                            // one per CTA
+    uint64_t *tmem_empty = accum_full + 1;                                       // leader's is used
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const long tile_row = (long)blockIdx.y * TN;              // slab-relative first cell of the tile
+    const long i0 = i_first + tile_row;
+    const long blk = (long)(blockIdx.x >> 1) * 2 + rank;      // this CTA's block of 127 signatures
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);                           // the leader's expect_tx; both CTAs' TMA bytes land on it
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        mbar_init(tmem_empty, 2 * GEN_WARPS);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_values);
+        tma_prefetch_desc(&tmap_weights);
+    }
+    if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+    if (tid >= 64 && tid - 64 < TN) den_s[tid - 64] = 0.0;
+    tc_fence_before_sync();
+    cluster_sync();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer: this CTA's 128 value rows and
+        // its 64 of the tile's 128 weight rows, all signalled on the leader's barrier
+        if (lane == 0) {
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * L::stage_bytes);
+                const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
+                uint8_t *dst = smem + s * L::stage_bytes;
+#pragma unroll
+                for (int b = 0; b < SR; ++b)
+                    tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS, (int)(b * Kpad + blk * TM),
+                                     leader_full);
+#pragma unroll
+                for (int a = 0; a < WD; ++a)
+                    tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
+                                     (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (leader CTA)
+        if (rank == 0) {
+            const uint32_t idesc = idesc_i8(2 * TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
+            const uint64_t a_desc_base = smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
+            const uint64_t b_desc_base = smem_desc(smem_u32(smem) + SR * A_PLANE_BYTES, 16, 1024, LAYOUT_SW128);
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int chunk = it / chunk_stages;
+                const bool chunk_first = it % chunk_stages == 0;
+                if (chunk_first && chunk > 0) {
+                    mbar_wait_cluster(tmem_empty, (chunk - 1) & 1);     // epilogues of both CTAs drained TMEM
+                    tc_fence_after_sync();
+                }
+                mbar_wait_cluster(&full[s], ph);              // both CTAs' operands of this stage
+                tc_fence_after_sync();
+                if (elect_one()) {
+                    const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                    const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                    if (!(dbg & 1)) {
+                        // K step ks: 32 bytes further along the swizzled rows of both operands
+                        if (chunk_first)
+                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
+                        else
+                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
+#pragma unroll
+                        for (int ks = 1; ks < KS / 32; ++ks)
+                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2), idesc);
+                    }
+                    umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
+                    if (it % chunk_stages == chunk_stages - 1 || it == n_stages - 1) umma_commit_pair(accum_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue warps (drain at the end of every j chunk)
+        const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31
+        const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const int row = quad * 32 + lane;
+        const long sig = blk * SIGS_PER_TILE + row;
+        const bool row_live = row < SIGS_PER_TILE && sig < K;
+        const int n_chunks = (n_stages + chunk_stages - 1) / chunk_stages;
+#pragma unroll 1
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const bool last = chunk == n_chunks - 1;
+            mbar_wait(accum_full, chunk & 1);
+            tc_fence_after_sync();
+            // phase A: the ones row (tile row 127) accumulates sum_j W_ij of every column
+            if (quad == 3) {
+#pragma unroll 1
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = part * 32 + b * 16;
+                    uint32_t acc[NCLASS][16];
+#pragma unroll
+                    for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                    tmem_ld_wait();
+                    if (lane == 31) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            long long d = 0;
+#pragma unroll
+                            for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                            den_s[col0 + e] += (double)d;
+                        }
+                    }
+                }
+            }
+            named_barrier_sync(1, GEN_THREADS);
+            const Digits dg = decode_range<SR>(range);
+            // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
+            const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
+            const bool invalid = *flag != 0;
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+                const int col0 = part * 32 + b * 16;
+                uint32_t acc[NCLASS][16];
+#pragma unroll
+                for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                tmem_ld_wait();
+                if (row_live) {
+                    const long ibase = i0 + col0;
+                    double *orow = out + sig * ld_out + ibase;
+                    const double *vrow = values + sig * ld + ibase;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        if (ibase + e >= N) continue;
+                        long long num = 0;
+#pragma unroll
+                        for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                        // partial sums of earlier j chunks are parked in the output row
+                        double total = (double)num;
+                        if (chunk > 0) total += orow[e];
+                        if (!last) {
+                            orow[e] = total;
+                            continue;
+                        }
+                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
+                        // zero row sum -> prediction 0 (Signatures.py:400-402)
+                        const double den = den_s[col0 + e];
+                        double r = den > 0.0 ? 0.5 * ((total / den) * inv_scale + centre) : 0.0;
+                        if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
+                        if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
+                        orow[e] = r;
+                    }
+                }
+            }
+            if (!last) {
+                // TMEM may be overwritten by the next chunk once every epilogue warp of the pair is done
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
+            }
+        }
+    }
+    tc_fence_before_sync();
+    cluster_sync();
+    if (warp == 0) tmem_dealloc_pair(tmem, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -624,8 +884,32 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Plan {
     int sr;
     long nblk, Kpad, Npad;
-    size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, total;
+    long slab_tiles;                             // cell tiles (128 cells i) whose weight planes are resident at once
+    size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, weights_off, total;
 };
+
+constexpr size_t kWeightSlabBudget = 6ull << 30;   // bytes of generated weight planes kept at a time
+
+// Tiles per slab: as many as the budget holds, trimmed so that the CTA pairs of one slab fill
+// whole waves of the machine (a slab is one launch; its last wave should not run half empty).
+long pick_slab_tiles(long n_tiles, long sig_pairs, long Npad) {
+    const size_t tile_bytes = (size_t)WD * TN * Npad;
+    long cap = (long)(kWeightSlabBudget / tile_bytes);
+    if (cap < 1) cap = 1;
+    if (cap >= n_tiles) return n_tiles;
+    const long pairs_per_wave = fp::sm_count() / 2;
+    long best = cap;
+    double best_fill = 0.0;
+    for (long t = cap; t >= 1 && t > cap / 2; --t) {
+        const long items = t * sig_pairs, waves = (items + pairs_per_wave - 1) / pairs_per_wave;
+        const double fill = (double)items / (double)(waves * pairs_per_wave);
+        if (fill > best_fill + 1e-9) {
+            best_fill = fill;
+            best = t;
+        }
+    }
+    return best;
+}
 
 bool make_plan(long N, long K, Plan *p) {
     if (N > 4000000) return false;               // three balanced digits hold |r * scale| <= 8 355 711
@@ -646,6 +930,9 @@ bool make_plan(long N, long K, Plan *p) {
     p->flag_off = off;
     p->range_off = off + 64;
     off += 1024;
+    p->slab_tiles = pick_slab_tiles(p->Npad / TN, p->nblk / 2, p->Npad);
+    p->weights_off = off;
+    off += align_up((size_t)WD * p->slab_tiles * TN * p->Npad, 1024);
     p->total = off;
     return true;
 }
@@ -718,7 +1005,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
                                                                             p.Npad, nn, ci, cj);
         FP_CHECK_LAUNCH("cell_setup_kernel");
     }
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_w;
     {
         cuuint64_t dims[2] = {(cuuint64_t)p.Npad, (cuuint64_t)(p.sr * p.Kpad)};
         cuuint64_t strides[1] = {(cuuint64_t)p.Npad};
@@ -732,25 +1019,69 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
             return FP_ECUDA;
         }
     }
+    const int n_stages = (int)(p.Npad / KS);
+    const int dbg = getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0;
+    static const bool fused = getenv("FP_TC_FUSED") && atoi(getenv("FP_TC_FUSED")) != 0;
     static bool attr_set = false;
     if (!attr_set) {
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            SmemLayout<2>::total));
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            SmemLayout<3>::total));
+        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           MmaSmem<2>::total));
+        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           MmaSmem<3>::total));
         attr_set = true;
     }
-    const int n_stages = (int)(p.Npad / KS);
-    const int dbg = getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0;
-    // x: pair index (cell tile) * 2 + CTA rank in the pair; y: pair of signature blocks
-    dim3 grid((unsigned)(2 * ((N + TN - 1) / TN)), (unsigned)(p.nblk / 2));
-    if (p.sr == 2)
-        consistency_tc_kernel<2><<<grid, THREADS, SmemLayout<2>::total, st>>>(
-            tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, n_stages, output_kind, range, flag, dbg);
-    else
-        consistency_tc_kernel<3><<<grid, THREADS, SmemLayout<3>::total, st>>>(
-            tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, CHUNK_STAGES_3, output_kind, range, flag,
-            dbg);
-    FP_CHECK_LAUNCH("consistency_tc_kernel");
+    if (fused) {
+        // x: pair index (cell tile) * 2 + CTA rank in the pair; y: pair of signature blocks
+        dim3 grid((unsigned)(2 * ((N + TN - 1) / TN)), (unsigned)(p.nblk / 2));
+        if (p.sr == 2)
+            consistency_tc_kernel<2><<<grid, THREADS, SmemLayout<2>::total, st>>>(
+                tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, n_stages, output_kind, range, flag,
+                dbg);
+        else
+            consistency_tc_kernel<3><<<grid, THREADS, SmemLayout<3>::total, st>>>(
+                tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, CHUNK_STAGES_3, output_kind, range,
+                flag, dbg);
+        FP_CHECK_LAUNCH("consistency_tc_kernel");
+        return FP_OK;
+    }
+    uint8_t *wplanes = reinterpret_cast<uint8_t *>(ws + p.weights_off);
+    const long plane_rows = p.slab_tiles * TN;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.Npad, (cuuint64_t)(WD * plane_rows)};
+        cuuint64_t strides[1] = {(cuuint64_t)p.Npad};
+        cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)TNH};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wplanes, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fp::set_error("fp_consistency: cuTensorMapEncodeTiled (weights) failed (%d)", (int)r);
+            return FP_ECUDA;
+        }
+    }
+    const long n_tiles = p.Npad / TN;
+    for (long t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
+        const long tiles = n_tiles - t0 < p.slab_tiles ? n_tiles - t0 : p.slab_tiles;
+        const long i_first = t0 * TN, slab_rows = tiles * TN;
+        dim3 ggrid((unsigned)((p.Npad / WG_COLS + WG_THREADS - 1) / WG_THREADS), (unsigned)(slab_rows / WG_ROWS));
+        weight_planes_kernel<<<ggrid, WG_THREADS, 0, st>>>(ci, cj, i_first, slab_rows, plane_rows, p.Npad, wplanes);
+        FP_CHECK_LAUNCH("weight_planes_kernel");
+        // x: pair of signature blocks * 2 + CTA rank in the pair (fastest: the pairs in flight share
+        // a cell tile and with it the weight planes in L2); y: cell tile of the slab
+        dim3 grid((unsigned)p.nblk, (unsigned)tiles);
+        if (p.sr == 2)
+            consistency_mma_kernel<2><<<grid, THREADS, MmaSmem<2>::total, st>>>(
+                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_stages, n_stages,
+                output_kind, range, flag, dbg);
+        else
+            consistency_mma_kernel<3><<<grid, THREADS, MmaSmem<3>::total, st>>>(
+                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_stages, CHUNK_STAGES_3,
+                output_kind, range, flag, dbg);
+        FP_CHECK_LAUNCH("consistency_mma_kernel");
+    }
     return FP_OK;
 }
