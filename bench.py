@@ -293,7 +293,9 @@ def run_b200(args):
     score_bytes = G * N * 16.0 + N * n_rows * 8.0 + 5.0 * nnz  # per launch
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of
     # this exact configuration (profiles/r01_summary_tc.md); None where no capture exists
-    ncu_traffic = {("C2", "tc", 1): 726867712 + 552165376, ("C2", "fp64", 1): 603465984 + 551192064}
+    # (tc: weight_planes_kernel 0.0013 + 1.5579 GB and consistency_mma_kernel 7.5027 + 0.6680 GB)
+    ncu_traffic = {("C2", "tc", 1): 1338000 + 1557907000 + 7502659000 + 667994000,
+                   ("C2", "fp64", 1): 603465984 + 551192064}
     roofline = dict(bound="tensor", kernel="fp_consistency[%s]" % precision,
                     achieved=cons_flops / (cons_ms * 1e-3) / 1e12, peak=peaks["tflops"],
                     unit="TFLOP/s", traffic=ncu_traffic.get((args.workload, precision, 1)),
@@ -349,8 +351,8 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
     import fastproject_b200 as FP
     # two sets of pinned host buffers: consecutive steps are different host arrays, so every
-    # step uploads its own inputs; at one GPU the upload of step k+1 is started inside step k's
-    # sigs_vs_projections(prefetch_next=...) and overlaps its projection loop
+    # step uploads its own inputs; the upload of step k+1 is started at the beginning of step k
+    # (fastproject_b200.prefetch) and runs behind the whole step
     host = []
     for _ in range(2):
         xh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
@@ -359,27 +361,35 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
         host.append(synth.ExpressionMatrix(xh.numpy(), wh.numpy(), wl["genes"], wl["cells"]))
     torch.cuda.synchronize()
     # a pipeline needs a few steps to show its steady state; the first timed step still uploads
-    # its matrices synchronously
-    steps = max(args.steps, 6)
+    # its matrices synchronously (its share shrinks with the number of steps)
+    steps = max(args.steps, 12)
+    warm = max(args.warmup, 3)
     d2h = 0
 
     def one_step(data, nxt):
+        # this step's matrices first (a no-op when the previous step already started their
+        # upload), then the NEXT step's: queued on the copy engine right behind, so the engine
+        # never idles and never serves the later data set first
+        FP.prefetch(data.base, data.weights, replicated=world > 1)
+        if nxt is not None:
+            FP.prefetch(nxt.base, nxt.weights, replicated=world > 1)
         real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5, distributed=world > 1)
         rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5, distributed=world > 1)
         res = S.sigs_vs_projections(wl["projections"], real, rnd, SIGMA, precision=precision,
-                                    distributed=world > 1,
-                                    prefetch_next=None if nxt is None else (nxt.base, nxt.weights))
+                                    distributed=world > 1)
         first = next(iter(real.values()))
         host_scores = first._batch.host_scores()                 # D2H of all real scores
         E.expression_cache.evict(data.base)
         E.expression_cache.evict(data.weights)
         return real, rnd, host_scores.nbytes + res[2].nbytes + res[3].nbytes + res[4].nbytes
 
-    # warm-up step (untimed), then ``steps`` timed steps back to back; every timed step's inputs
-    # cross PCIe inside the timed region (the first one synchronously, the others prefetched
-    # during the previous step)
+    # warm-up steps (untimed, pipelined like the timed ones: they also grow the pinned staging
+    # pools and the allocator caches to their steady size), then everything resident is dropped
+    # and ``steps`` timed steps run back to back; every timed step's inputs cross PCIe inside the
+    # timed region (the first one synchronously, the others prefetched during the previous step)
     E.clear_device_cache()
-    real, rnd, d2h = one_step(host[0], None)
+    for it in range(warm):
+        real, rnd, d2h = one_step(host[it % len(host)], host[(it + 1) % len(host)] if it + 1 < warm else None)
     E.clear_device_cache()
     torch.cuda.synchronize()
     if world > 1:
@@ -408,7 +418,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
             "d2h_bytes_per_step": int(d2h) * world, "s_per_step": t, "steps": len(times),
             "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections(distributed=%s), "
                    "pinned host inputs; steps back to back, the upload of the next step's matrices "
-                   "(prefetch_next=) overlaps the projection loop of the current one%s"
+                   "(fastproject_b200.prefetch at the start of the step) overlaps the current step%s"
                    % (world > 1, "; the expression matrices are one data set per job: every rank uploads "
                       "1/world of the rows over its PCIe link and the rows are all-gathered over NVLink"
                       if world > 1 else "")}

@@ -54,6 +54,36 @@ def resolve_precision(precision, n):
 # --------------------------------------------------------------------------
 # host -> device
 # --------------------------------------------------------------------------
+_SMALL_UPLOAD = 16 << 20       # host arrays up to this size bypass the copy engine
+_small_pool = []               # [pinned uint8 tensor, event of its last use]
+
+
+def _pinned_slot(nbytes):
+    """A pinned staging buffer no kernel is reading any more (or a new one)."""
+    for slot in _small_pool:
+        if slot[0].numel() >= nbytes and slot[1].query():
+            return slot
+    size = max(1 << 20, 1 << (int(nbytes) - 1).bit_length())
+    slot = [torch.empty((size,), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()]
+    _small_pool.append(slot)
+    return slot
+
+
+def _pull_small(a, dev):
+    """NumPy array (C-contiguous, <= _SMALL_UPLOAD bytes) -> CUDA tensor of the same dtype,
+    fetched by a kernel from a pinned staging buffer (``fp_pull_host``): the per-call tables
+    of the path do not queue behind a multi-gigabyte prefetch on the copy engine."""
+    nbytes = a.nbytes
+    out = torch.empty(tuple(a.shape), dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype, device=dev)
+    if nbytes == 0:
+        return out
+    slot = _pinned_slot(nbytes)
+    slot[0].numpy()[:nbytes] = a.reshape(-1).view(np.uint8)
+    _native.call("fp_pull_host", ptr(out), ptr(slot[0]), nbytes, stream_ptr())
+    slot[1].record()
+    return out
+
+
 def to_device(arr, dtype=torch.float64):
     """NumPy array or CPU/GPU torch tensor -> contiguous CUDA tensor."""
     dev = require_cuda()
@@ -65,6 +95,8 @@ def to_device(arr, dtype=torch.float64):
             a = a.astype(np.float64)
         if not a.flags["C_CONTIGUOUS"]:
             a = np.ascontiguousarray(a)
+        if a.nbytes <= _SMALL_UPLOAD and a.dtype.kind in "fiu" and a.dtype.byteorder in "=|<":
+            return _pull_small(a, dev).to(dtype=dtype).contiguous()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", UserWarning)     # read-only arrays: we only read them
             t = torch.from_numpy(a)
@@ -107,14 +139,24 @@ _PINNED_CHUNK = 32 << 20
 _pinned = []
 
 
+_PINNED_RESULT_MAX = 1 << 30
+
+
 def to_host(dev_tensor):
-    """CUDA tensor (any strides) -> fresh NumPy array, staged through two reusable pinned
-    buffers: a ``.cpu()`` into pageable memory runs at a few GB/s, this at PCIe speed with
-    the host-side memcpy overlapped."""
+    """CUDA tensor (any strides) -> NumPy array.  Results up to 1 GiB land directly in a pinned
+    host tensor that the returned array views (one DMA at PCIe speed, no second host copy; the
+    pinned block goes back to torch's host allocator when the array is released).  Larger ones
+    are staged through two reusable pinned buffers into pageable memory -- a plain ``.cpu()``
+    into pageable memory runs at a few GB/s."""
+    if dev_tensor.dtype != torch.float64 or dev_tensor.numel() * 8 < (1 << 20):
+        return dev_tensor.cpu().numpy()
+    if dev_tensor.numel() * 8 <= _PINNED_RESULT_MAX:
+        host = torch.empty(tuple(dev_tensor.shape), dtype=torch.float64, pin_memory=True)
+        host.copy_(dev_tensor, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
     t = dev_tensor.contiguous()
-    out = np.empty(tuple(t.shape), dtype=np.float64 if t.dtype == torch.float64 else None)
-    if t.dtype != torch.float64 or t.numel() * 8 < (4 << 20):
-        return t.cpu().numpy()
+    out = np.empty(tuple(t.shape), dtype=np.float64)
     flat_dev = t.view(-1)
     flat_out = out.reshape(-1)
     n = flat_dev.numel()
@@ -210,9 +252,9 @@ class _ExpressionCache(object):
         The host -> device copy engine serves transfers in submission order (measured: the
         kilobyte-sized uploads of a running step -- index tables, coordinates -- waited ~90 ms
         behind a queued 4.8 GB prefetch and stalled the compute stream; feeding the engine in
-        paced pieces from a Python thread halved the copy rate).  So issue the prefetch at a
-        point after which the running step uploads nothing more:
-        ``sigs_vs_projections(..., prefetch_next=...)`` does it right before its projection loop."""
+        paced pieces from a Python thread halved the copy rate).  The small tables of the path
+        therefore do not use the copy engine at all (``_pull_small``), and a prefetch can be
+        issued at any point -- best at the very start of the step it overlaps."""
         if isinstance(a, torch.Tensor) and a.is_cuda:
             return
         dev = require_cuda()

@@ -6,6 +6,7 @@
 from __future__ import annotations
 
 import itertools
+import operator
 
 import numpy as np
 import torch
@@ -76,8 +77,11 @@ def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject
     lengths = np.fromiter((len(d) for d in dicts), dtype=np.int64, count=len(dicts))
     flat_genes = list(itertools.chain.from_iterable(dicts))
     flat_vals = list(itertools.chain.from_iterable(d.values() for d in dicts))
-    rows = np.fromiter(map(index.get, flat_genes, itertools.repeat(-1)), dtype=np.int64,
-                       count=len(flat_genes))
+    try:                                   # one C call when every gene is on the matrix
+        rows = np.array(operator.itemgetter(*flat_genes)(index), dtype=np.int64).reshape(-1)
+    except (KeyError, TypeError):          # a gene that is not on the matrix / no genes at all
+        rows = np.fromiter(map(index.get, flat_genes, itertools.repeat(-1)), dtype=np.int64,
+                           count=len(flat_genes))
     try:
         vals = np.fromiter(flat_vals, dtype=np.float64, count=len(flat_vals))
     except (TypeError, ValueError):

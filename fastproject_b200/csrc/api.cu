@@ -78,3 +78,31 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
     fp::set_error("fp_consistency: unknown precision mode %d", precision_mode);
     return FP_EUNSUPPORTED;
 }
+
+namespace {
+__global__ void __launch_bounds__(256) pull_host_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16,
+                                                        size_t tail_bytes) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < tail_bytes)
+        reinterpret_cast<unsigned char *>(dst + n16)[threadIdx.x] =
+            reinterpret_cast<const unsigned char *>(src + n16)[threadIdx.x];
+}
+}  // namespace
+
+extern "C" int fp_pull_host(void *dst_device, const void *src_pinned_host, size_t bytes, void *stream) {
+    fp::clear_error();
+    if (bytes == 0) return FP_OK;
+    FP_CHECK_ARG(dst_device && src_pinned_host, "fp_pull_host: null pointer");
+    FP_CHECK_ARG(((reinterpret_cast<uintptr_t>(dst_device) | reinterpret_cast<uintptr_t>(src_pinned_host)) & 15) == 0,
+                 "fp_pull_host: pointers must be 16-byte aligned");
+    const size_t n16 = bytes / 16;
+    size_t blocks = (n16 + 255) / 256;
+    const size_t cap = (size_t)fp::sm_count() * 4;       // many loads in flight: PCIe reads are latency bound
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pull_host_kernel<<<(unsigned)blocks, 256, 0, fp::as_stream(stream)>>>(
+        static_cast<uint4 *>(dst_device), static_cast<const uint4 *>(src_pinned_host), n16, bytes % 16);
+    FP_CHECK_LAUNCH("pull_host_kernel");
+    return FP_OK;
+}

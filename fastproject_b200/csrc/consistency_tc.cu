@@ -14,9 +14,11 @@
 //   * m_i = min_{j != i} d_ij^2 (nearest neighbour): a per-row scale that cancels
 //     in the quotient and puts the largest weight of every row at exactly 1;
 //   * W_ij = round(w_ij * (2^32 - 1)) is a 32-bit fixed-point weight, generated
-//     on the fly in FP64 (table + cubic for 2^t, |error| < 2^-33) by the CUDA
-//     cores of the CTA that consumes it and written straight into shared
-//     memory as four unsigned 8-bit digit planes (the UMMA B operand);
+//     in FP64 (table + cubic for 2^t, |error| < 2^-33) ONCE per projection by
+//     weight_planes_kernel and stored as four unsigned 8-bit digit planes
+//     [digit][cell i][cell j] (the UMMA B operand) -- 4 bytes per weight, 1.6 GB
+//     at 20 000 cells, generated in slabs of cells i when N x N x 4 bytes exceeds
+//     the slab budget (100 000 and 1 000 000 cells);
 //   * the values are half-integers (average ranks, one-hot / binary columns), so
 //     r_j = (2 v_j - centre) * 2^shift is an integer (centre and shift from the value
 //     range: N + 1 for ranks; the top digit is always well used); it is cut into two
@@ -32,13 +34,19 @@
 //     use identical quantised weights (the quotient is an exact weighted mean
 //     with weights perturbed by < 2^-33 relative to the row maximum).
 //
-// Tile: a PAIR of CTAs (cluster of 2, tcgen05 cta_group::2) owns 2 x 128 signature rows
-// (M = 256) x 128 cells; j is streamed in stages of 128.  Each CTA loads the value planes
-// of its own 128 rows by TMA and GENERATES the weights of 64 of the 128 cells -- the MMA
-// reads the B operand from both CTAs' shared memory, so every generated weight feeds 254
-// signatures.  4 classes x 128 columns = all 512 TMEM columns of each SM.  Warp roles:
-// warp 0 TMA producer, warp 1 MMA issuer (leader CTA, one elected lane), warps 2-17 weight
-// generators, then epilogue.  The FP64 verifier lives in consistency_fp64.cu.
+// Tile (consistency_mma_kernel): a PAIR of CTAs (cluster of 2, tcgen05 cta_group::2) owns
+// 2 x 128 signature rows (M = 256) x 128 cells i; j is streamed in stages of 128.  Each CTA
+// loads by TMA (128-byte swizzle) the value planes of its own 128 rows and the weight planes
+// of 64 of the 128 cells -- the MMA reads the B operand from both CTAs' shared memory.
+// 4 classes x 128 columns = all 512 TMEM columns of each SM.  Warp roles: warp 0 TMA
+// producer, warp 1 MMA issuer (leader CTA, one elected lane), warps 2-17 epilogue.  The
+// launch puts the pairs of signature blocks of one cell tile next to each other, so the
+// pairs in flight stream the same weight planes and all but the first read them from L2.
+// (Until round 1's last sessions the weights were generated inside this kernel by 16
+// generator warps and never left shared memory; every pair of signature blocks then
+// regenerated the whole N x N matrix -- 14 times at 3 500 signatures -- and the FP64 generator,
+// not the tensor pipe, bounded the kernel: 14.0 ms per projection against 7.5 ms now.)
+// The FP64 verifier lives in consistency_fp64.cu.
 #include <stdlib.h>
 
 #include "fp_common.cuh"
@@ -51,12 +59,12 @@ using namespace fp::tc;
 constexpr int TM = 128;            // signature rows per CTA (127 + the ones row)
 constexpr int SIGS_PER_TILE = 127;
 constexpr int TN = 128;            // cells i per CTA pair
-constexpr int TNH = TN / 2;        // cells whose weights one CTA generates
+constexpr int TNH = TN / 2;        // cells whose weight planes one CTA of the pair loads
 constexpr int KS = 128;            // cells j per stage (bytes of K per digit plane)
 constexpr int WD = 4;              // weight digits (32-bit fixed point)
-constexpr int GEN_WARPS = 16;
-constexpr int GEN_THREADS = GEN_WARPS * 32;
-constexpr int THREADS = 64 + GEN_THREADS;
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quadrant
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_PLANE_BYTES = TM * KS;    // 16 KB: one value digit plane, one stage
 constexpr int B_PLANE_BYTES = TNH * KS;   //  8 KB: one weight digit plane of this CTA's 64 cells
 constexpr int NCLASS = 4;
@@ -65,17 +73,6 @@ constexpr int TAB_COPIES = 16;     // ... 16 interleaved copies (lanes l and l+1
                                    // 64-entry table were measured: no faster)
 // s32 accumulators: a class sums at most 3 digit products of magnitude <= 255 * 128 per j
 constexpr int CHUNK_STAGES_3 = 128;       // three value digits: drain every 16 384 cells j
-
-template <int SR>
-struct SmemLayout {
-    static constexpr int stages = SR == 2 ? 3 : 2;
-    static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
-    static constexpr int table_off = stages * stage_bytes;
-    static constexpr int jrec_off = table_off + TAB * TAB_COPIES * 8;       // per generator warp: 16 CellJ
-    static constexpr int den_off = jrec_off + 2 * GEN_WARPS * 16 * 32;      // double buffered
-    static constexpr int bar_off = den_off + TN * 8;
-    static constexpr int total = bar_off + 256;   // 18 mbarriers + the TMEM slot
-};
 
 // cell records prepared by cell_setup_kernel
 struct __align__(32) CellI { double alpha, c, x2c, y2c; };   // row side
@@ -318,295 +315,11 @@ __device__ __forceinline__ void issue_k_step(uint32_t tmem, uint64_t a_desc0, ui
         }
 }
 
-template <int SR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-consistency_tc_kernel(const __grid_constant__ CUtensorMap tmap_planes, const CellI *__restrict__ ci,
-                      const CellJ *__restrict__ cj, const double *__restrict__ values, long ld,
-                      double *__restrict__ out, long ld_out, long N, long K, long Kpad, int n_stages,
-                      int chunk_stages, int output_kind, const unsigned long long *__restrict__ range,
-                      const int *__restrict__ flag, int dbg) {
-    using L = SmemLayout<SR>;
-    constexpr int STAGES = L::stages;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = smem_raw;                                 // 1024-aligned (128-byte swizzle atoms)
-    double *tab = reinterpret_cast<double *>(smem + L::table_off);
-    double *den_s = reinterpret_cast<double *>(smem + L::den_off);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES] leader's are used
-    uint64_t *empty = full + 4;                                                  // [STAGES] one per CTA
-    uint64_t *bready = empty + 4;                                                // [STAGES] one per CTA
-    uint64_t *accum_full = bready + 4;                                           // one per CTA
-    uint64_t *tmem_empty = accum_full + 1;                                       // leader's is used
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();                  // 0 = leader of the pair
-    const long i0 = (long)(blockIdx.x >> 1) * TN;             // first cell of the pair's tile
-    const long blk = (long)blockIdx.y * 2 + rank;             // this CTA's block of 127 signatures
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 2);                           // leader's TMA thread + the peer's relay warp
-            mbar_init(&empty[s], 1);
-            mbar_init(&bready[s], GEN_WARPS);                 // this CTA's generator warps
-        }
-        mbar_init(accum_full, 1);
-        mbar_init(tmem_empty, 2 * GEN_WARPS);
-        mbar_fence_init();
-        tma_prefetch_desc(&tmap_planes);
-    }
-    if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
-    if (tid >= 64) {
-        for (int idx = tid - 64; idx < TAB * TAB_COPIES; idx += GEN_THREADS)
-            tab[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
-        if (tid - 64 < TN) den_s[tid - 64] = 0.0;
-    }
-    tc_fence_before_sync();
-    cluster_sync();                                           // barriers of both CTAs are initialised
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------ TMA producer (value digit planes of this CTA's rows)
-        if (lane == 0) {
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                if (dbg & 128) mbar_spin(&empty[s], ph ^ 1); else
-                mbar_wait(&empty[s], ph ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * SR * A_PLANE_BYTES);
-                const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
-                uint8_t *dst = smem + s * L::stage_bytes;
-#pragma unroll
-                for (int b = 0; b < SR; ++b)
-                    tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_planes, it * KS, (int)(b * Kpad + blk * TM),
-                                     leader_full);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (rank != 0) {
-            // -------------------------------------------- relay (peer CTA): one cluster-scope release per
-            // stage tells the leader that this CTA's half of the weight tile is in shared memory
-            // (a cluster-scope release costs a MEMBAR.GPU + L1 invalidate: kept off the generators)
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&bready[s], (it / STAGES) & 1);
-                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&full[s]), 0));
-                __syncwarp();
-            }
-        }
-        // ------------------------------------------------ MMA issuer (leader CTA)
-        if (rank == 0) {
-            const uint32_t idesc = idesc_i8(2 * TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
-            const uint64_t a_desc_base = smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
-            const uint64_t b_desc_base = smem_desc(smem_u32(smem) + SR * A_PLANE_BYTES, TNH * 16, 128, LAYOUT_NONE);
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int chunk = it / chunk_stages;
-                const bool chunk_first = it % chunk_stages == 0;
-                if (chunk_first && chunk > 0) {
-                    mbar_wait_cluster(tmem_empty, (chunk - 1) & 1);     // epilogues of both CTAs drained TMEM
-                    tc_fence_after_sync();
-                }
-                if (dbg & 128) {
-                    mbar_spin(&bready[s], ph);
-                    mbar_spin_cluster(&full[s], ph);
-                } else {
-                mbar_wait(&bready[s], ph);                    // own generators
-                mbar_wait_cluster(&full[s], ph);              // value planes of both CTAs + the peer's weights
-                }
-                tc_fence_after_sync();
-                if (elect_one()) {
-                    const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
-                    const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
-                    if (!(dbg & 1)) {
-                        // K step ks: 32 bytes further along the swizzled A rows, two 16-byte chunks
-                        // (2 * TNH * 16 bytes) further in the B planes
-                        if (chunk_first)
-                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
-                        else
-                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
-#pragma unroll
-                        for (int ks = 1; ks < KS / 32; ++ks)
-                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * (2 * TNH)),
-                                                    idesc);
-                    }
-                    umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
-                    if (it % chunk_stages == chunk_stages - 1 || it == n_stages - 1) umma_commit_pair(accum_full);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ------------------------------------------------ weight generators (B operand, 64 cells of the tile)
-        // generator warps 2w, 2w+1 own the 16-byte K chunk w of every stage (16 cells j): one the
-        // cells 0-31, the other the cells 32-63 of this CTA's half tile; one cell per lane.
-        const int kchunk = (warp - 2) >> 1;
-        const int cell = ((warp - 2) & 1) * 32 + lane;         // row of the B planes
-        const long gi = i0 + rank * TNH + cell;                 // global cell index
-        const char *my_tab = reinterpret_cast<const char *>(tab + (lane & (TAB_COPIES - 1)));
-        const CellI me = ci[gi];
-        // the 16 column records of this warp's chunk go through a private, double-buffered
-        // 512-byte slot of shared memory (broadcast reads); cp.async brings the next stage's
-        // records in while this stage is computed -- no registers held across the L2 latency
-        CellJ *jslot = reinterpret_cast<CellJ *>(smem + L::jrec_off) + (warp - 2) * 32;
-        const char *jsrc = reinterpret_cast<const char *>(cj + kchunk * 16) + lane * 16;
-        auto prefetch_records = [&](int it_next) {
-            const uint32_t dst = smem_u32(reinterpret_cast<char *>(jslot + (it_next & 1) * 16) + lane * 16);
-            const char *src = jsrc + (long)it_next * KS * sizeof(CellJ);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        prefetch_records(0);
-        const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31
-        const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
-        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        const int row = quad * 32 + lane;
-        const long sig = blk * SIGS_PER_TILE + row;
-        const bool row_live = row < SIGS_PER_TILE && sig < K;
-
-        const int n_chunks = (n_stages + chunk_stages - 1) / chunk_stages;
-#pragma unroll 1
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
-          const int it_end = min(n_stages, (chunk + 1) * chunk_stages);
-#pragma unroll 1
-          for (int it = chunk * chunk_stages; it < it_end; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            const long jbase = (long)it * KS + kchunk * 16;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();                                      // records of stage it visible; slot of it+1 free
-            if (it + 1 < n_stages && !(dbg & 32)) prefetch_records(it + 1);
-            const CellJ *jr = jslot + (it & 1) * 16;
-            // two halves of 8 cells j: the byte planes are packed as soon as 8 weights exist,
-            // which keeps the live register set small (576 threads leave 96 registers each)
-            uint32_t pk[WD][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t w[8];
-                if (dbg & 2) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) w[e] = 0x01020304u * (e + it);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const double2 xy = *reinterpret_cast<const double2 *>(jr + h * 8 + e);
-                        const double nb = jr[h * 8 + e].nb;
-                        double t = fma(me.c, nb, me.alpha);
-                        t = fma(me.x2c, xy.x, t);
-                        t = fma(me.y2c, xy.y, t);
-                        w[e] = weight_fixed32(t, my_tab);
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < WD; ++a) {
-                    const uint32_t sel = (3 - a) * 0x11 + 0x40;   // byte (3-a) of x, byte (3-a) of y
-                    pk[a][2 * h] = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
-                    pk[a][2 * h + 1] = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
-                }
-            }
-            if (dbg & 128) mbar_spin(&empty[s], ph ^ 1);
-            else mbar_wait(&empty[s], ph ^ 1);
-            uint8_t *bst = smem + s * L::stage_bytes + SR * A_PLANE_BYTES;
-#pragma unroll
-            for (int a = 0; a < WD; ++a)
-                if (!(dbg & 64) || pk[a][0] == 0x12345u)
-                    *reinterpret_cast<uint4 *>(bst + a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16) =
-                        make_uint4(pk[a][0], pk[a][1], pk[a][2], pk[a][3]);
-            // weights[diag] = 0 (Signatures.py:399): the cell's own column lies in one chunk of one
-            // stage; its four digit bytes are cleared after the store instead of testing every weight
-            const long dj = gi - jbase;
-            if (dj >= 0 && dj < 16) {
-#pragma unroll
-                for (int a = 0; a < WD; ++a) bst[a * B_PLANE_BYTES + (kchunk * TNH + cell) * 16 + dj] = 0;
-            }
-            if (!(dbg & 16)) fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bready[s]);
-          }
-
-            // -------------------------------------------- drain at the end of a j chunk / epilogue
-            const bool last = it_end == n_stages;
-            mbar_wait(accum_full, chunk & 1);
-            tc_fence_after_sync();
-            // phase A: the ones row (tile row 127) accumulates sum_j W_ij of every column
-            if (quad == 3) {
-#pragma unroll 1
-                for (int b = 0; b < 2; ++b) {
-                    const int col0 = part * 32 + b * 16;
-                    uint32_t acc[NCLASS][16];
-#pragma unroll
-                    for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
-                    tmem_ld_wait();
-                    if (lane == 31) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            long long d = 0;
-#pragma unroll
-                            for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
-                            den_s[col0 + e] += (double)d;
-                        }
-                    }
-                }
-            }
-            named_barrier_sync(1, GEN_THREADS);
-            const Digits dg = decode_range<SR>(range);
-            // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
-            const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
-            const bool invalid = *flag != 0;
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                const int col0 = part * 32 + b * 16;
-                uint32_t acc[NCLASS][16];
-#pragma unroll
-                for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
-                tmem_ld_wait();
-                if (row_live) {
-                    const long ibase = i0 + col0;
-                    double *orow = out + sig * ld_out + ibase;
-                    const double *vrow = values + sig * ld + ibase;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        if (ibase + e >= N) continue;
-                        long long num = 0;
-#pragma unroll
-                        for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
-                        // partial sums of earlier j chunks are parked in the output row
-                        double total = (double)num;
-                        if (chunk > 0) total += orow[e];
-                        if (!last) {
-                            orow[e] = total;
-                            continue;
-                        }
-                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
-                        // zero row sum -> prediction 0 (Signatures.py:400-402)
-                        const double den = den_s[col0 + e];
-                        double r = den > 0.0 ? 0.5 * ((total / den) * inv_scale + centre) : 0.0;
-                        if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
-                        if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
-                        orow[e] = r;
-                    }
-                }
-            }
-            if (!last) {
-                // TMEM may be overwritten by the next chunk once every epilogue warp of the pair is done
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
-            }
-        }
-    }
-    tc_fence_before_sync();
-    cluster_sync();                                           // no CTA of the pair leaves while the other may signal it
-    if (warp == 0) tmem_dealloc_pair(tmem, 512);
-}
-
-// ===========================================================================
-// Two-kernel form: the weight digit planes of a SLAB of cells i (all j) are generated once
-// into HBM / L2 and every block of signatures streams them by TMA, instead of every pair of
-// signature blocks regenerating them (14 times at 3 500 signatures).
-// ===========================================================================
+// ---------------------------------------------------------------------------
+// weight digit planes of a slab of cells i (all j): one thread owns 8 consecutive cells j
+// (their records stay in registers) and walks 32 cells i, so a warp stores 256 contiguous
+// bytes per digit plane and row.
+// ---------------------------------------------------------------------------
 constexpr int WG_THREADS = 256;
 constexpr int WG_COLS = 8;                 // cells j per thread: one 8-byte store per digit plane
 constexpr int WG_ROWS = 32;                // cells i per CTA
@@ -706,7 +419,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             mbar_init(&empty[s], 1);
         }
         mbar_init(accum_full, 1);
-        mbar_init(tmem_empty, 2 * GEN_WARPS);
+        mbar_init(tmem_empty, 2 * EPI_WARPS);
         mbar_fence_init();
         tma_prefetch_desc(&tmap_values);
         tma_prefetch_desc(&tmap_weights);
@@ -810,7 +523,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     }
                 }
             }
-            named_barrier_sync(1, GEN_THREADS);
+            named_barrier_sync(1, EPI_THREADS);
             const Digits dg = decode_range<SR>(range);
             // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
             const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
@@ -1021,32 +734,13 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
     }
     const int n_stages = (int)(p.Npad / KS);
     const int dbg = getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0;
-    static const bool fused = getenv("FP_TC_FUSED") && atoi(getenv("FP_TC_FUSED")) != 0;
     static bool attr_set = false;
     if (!attr_set) {
-        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           SmemLayout<2>::total));
-        FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           SmemLayout<3>::total));
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            MmaSmem<2>::total));
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            MmaSmem<3>::total));
         attr_set = true;
-    }
-    if (fused) {
-        // x: pair index (cell tile) * 2 + CTA rank in the pair; y: pair of signature blocks
-        dim3 grid((unsigned)(2 * ((N + TN - 1) / TN)), (unsigned)(p.nblk / 2));
-        if (p.sr == 2)
-            consistency_tc_kernel<2><<<grid, THREADS, SmemLayout<2>::total, st>>>(
-                tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, n_stages, output_kind, range, flag,
-                dbg);
-        else
-            consistency_tc_kernel<3><<<grid, THREADS, SmemLayout<3>::total, st>>>(
-                tmap, ci, cj, values, ld, out, ld_out, N, K, p.Kpad, n_stages, CHUNK_STAGES_3, output_kind, range,
-                flag, dbg);
-        FP_CHECK_LAUNCH("consistency_tc_kernel");
-        return FP_OK;
     }
     uint8_t *wplanes = reinterpret_cast<uint8_t *>(ws + p.weights_off);
     const long plane_rows = p.slab_tiles * TN;

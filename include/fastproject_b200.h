@@ -134,6 +134,17 @@ int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld,
                        int method, void *stream);
 
 /*
+ * fp_pull_host -- copy `bytes` bytes from PINNED host memory (cudaHostAlloc / cudaHostRegister,
+ * addressable by the device under unified addressing) to device memory with a kernel instead
+ * of the copy engine.  For the small per-call tables of the path (signature CSR arrays of
+ * Signatures.py:669-679, projection coordinates of :391-395): the copy engine serves requests
+ * in order, so a 2 MB table issued while the next data set's expression matrices (4.8 GB) are
+ * being uploaded would wait for all of it; SM loads over PCIe do not queue behind the engine.
+ * dst and src 16-byte aligned.
+ */
+int fp_pull_host(void *dst_device, const void *src_pinned_host, size_t bytes, void *stream);
+
+/*
  * fp_normalize_rows / fp_normalize_cols -- z-normalisation of every gene (row) or every
  * cell (column) of the genes x cells matrix: (x - mean) / std with population std and
  * std == 0 -> 1.  Replace NormalizationMethods.row_normalization (:34-41, the pipeline

@@ -18,11 +18,12 @@ for _ in range(2):
 torch.cuda.synchronize()
 def step(data, nxt, log):
     t = [time.perf_counter()]
+    if nxt is not None:
+        FP.prefetch(nxt.base, nxt.weights)
     real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5); t.append(time.perf_counter())
     t.append(time.perf_counter())
     rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5); t.append(time.perf_counter())
-    res = S.sigs_vs_projections(wl["projections"], real, rnd, 0.33,
-                                prefetch_next=None if nxt is None else (nxt.base, nxt.weights)); t.append(time.perf_counter())
+    res = S.sigs_vs_projections(wl["projections"], real, rnd, 0.33); t.append(time.perf_counter())
     hs = next(iter(real.values()))._batch.host_scores(); t.append(time.perf_counter())
     E.expression_cache.evict(data.base); E.expression_cache.evict(data.weights)
     log.append(["%.1f" % (1e3 * (b - a)) for a, b in zip(t[:-1], t[1:])])
