@@ -603,11 +603,21 @@ struct Plan {
 
 constexpr size_t kWeightSlabBudget = 6ull << 30;   // bytes of generated weight planes kept at a time
 
+// FASTPROJECT_B200_SLAB_BYTES overrides the budget (tests use it to run many slabs at small N)
+size_t weight_slab_budget() {
+    const char *e = getenv("FASTPROJECT_B200_SLAB_BYTES");
+    if (e) {
+        const long long v = atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return kWeightSlabBudget;
+}
+
 // Tiles per slab: as many as the budget holds, trimmed so that the CTA pairs of one slab fill
 // whole waves of the machine (a slab is one launch; its last wave should not run half empty).
 long pick_slab_tiles(long n_tiles, long sig_pairs, long Npad) {
     const size_t tile_bytes = (size_t)WD * TN * Npad;
-    long cap = (long)(kWeightSlabBudget / tile_bytes);
+    long cap = (long)(weight_slab_budget() / tile_bytes);
     if (cap < 1) cap = 1;
     if (cap >= n_tiles) return n_tiles;
     const long pairs_per_wave = fp::sm_count() / 2;

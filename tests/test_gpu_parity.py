@@ -176,6 +176,35 @@ def test_rank_short_keys_hard_cases(fp):
         assert np.array_equal(got[i, :1001], rankdata(y[i, :1001]))
 
 
+def test_small_uploads_bypass_copy_engine_bit_exact(fp):
+    """Per-call tables go host -> device through fp_pull_host (a kernel reading pinned memory):
+    every dtype / odd size must arrive byte for byte, also while a large copy is in flight."""
+    import torch
+    from fastproject_b200 import _engine as E
+    rng = np.random.RandomState(11)
+    big_host = torch.empty((64 << 20,), dtype=torch.uint8, pin_memory=True)
+    big_dev = torch.empty_like(big_host, device="cuda")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        big_dev.copy_(big_host, non_blocking=True)                  # keeps the copy engine busy
+    cases = [rng.normal(size=n) for n in (0, 1, 2, 3, 17, 4099, 200001)]
+    cases += [rng.randint(-100, 100, size=n).astype(np.int8) for n in (1, 15, 16, 17, 33333)]
+    cases += [rng.randint(0, 1 << 30, size=(7, 913)).astype(np.int32), rng.normal(size=(3, 5, 7)),
+              np.asfortranarray(rng.normal(size=(50, 60))), rng.uniform(size=1000) < 0.5]
+    for a in cases:
+        want = np.asarray(a, dtype=np.float64) if a.dtype == np.bool_ else a
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.int8): torch.int8,
+               np.dtype(np.int32): torch.int32}[want.dtype]
+        got = E.to_device(a, tdt).cpu().numpy()
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert np.array_equal(got, want)
+    # staging buffers are recycled only after the kernel that reads them has finished
+    outs = [(v, E.to_device(v)) for v in (rng.normal(size=50000) for _ in range(40))]
+    for v, d in outs:
+        assert np.array_equal(d.cpu().numpy(), v)
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------ kernels through the engine
 @pytest.mark.parametrize("n", [1, 2, 7, 64, 65, 1000, 4097])
 def test_row_medians_exact(fp, n):
@@ -313,6 +342,18 @@ def test_tensor_core_kernel_matches_fp64_kernel(fp, n, k, kw):
     # absolute error of the prediction, in rank units, relative to the rank range
     assert np.abs(a - b).max() <= 1e-7 * max(n, 16)
     np.testing.assert_allclose(np.median(b, axis=1), np.median(a, axis=1), rtol=0, atol=1e-8 * max(n, 16))
+
+
+@pytest.mark.parametrize("n,k,budget", [(1000, 260, 1 << 20), (4097, 130, 5 << 20), (33000, 3, 40 << 20)])
+def test_tensor_core_weight_slabs_do_not_change_the_result(fp, n, k, budget, monkeypatch):
+    """The weight digit planes are generated slab by slab (cells i) when N x N x 4 bytes exceeds
+    the budget (100 000+ cells).  Shrinking the budget runs the many-slab path at test sizes:
+    the output must be BIT-IDENTICAL to the one-slab run (same arithmetic, different staging)."""
+    a, one = _tc_case(fp, n, k, 77 + n, outliers=1)
+    monkeypatch.setenv("FASTPROJECT_B200_SLAB_BYTES", str(budget))
+    _, many = _tc_case(fp, n, k, 77 + n, outliers=1)
+    assert np.array_equal(one, many)
+    assert np.abs(a - one).max() <= 1e-7 * max(n, 16)
 
 
 def test_tensor_core_kernel_binary_predictions(fp):
