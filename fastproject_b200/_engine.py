@@ -362,6 +362,19 @@ def normalize_rows(x):
     return out
 
 
+def compute_weights(x, params, p_nd=None):
+    """[G x N] CUDA float64 expression, [4 x N] logistic parameters (x0, a, L, S), optional
+    [G x N] probability of non-detection (None: the zero mask) -> [G x N] weights."""
+    g, n = x.shape
+    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
+    params = params.contiguous()
+    nbytes = _native.query("fp_compute_weights_workspace_bytes", n)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _native.call("fp_compute_weights", ptr(x), ptr(p_nd), ptr(params), g, n, x.stride(0),
+                 0 if p_nd is None else p_nd.stride(0), ptr(out), n, ptr(ws), nbytes, stream_ptr())
+    return out
+
+
 def normalize_cols(x):
     """[G x N] CUDA float64 -> per-column z-scores (sequential row order), new tensor."""
     g, n = x.shape

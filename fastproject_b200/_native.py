@@ -36,6 +36,9 @@ SIGNATURES = {
     "fp_consistency_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
     "fp_consistency": (c_int, [c_ptr, c_ptr, c_f64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64,
                                c_int, c_int, c_ptr, c_size, c_ptr]),
+    "fp_compute_weights_workspace_bytes": (c_size, [c_i64]),
+    "fp_compute_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr,
+                                   c_size, c_ptr]),
     "fp_pull_host": (c_int, [c_ptr, c_ptr, c_size, c_ptr]),
     "fp_row_medians": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     "fp_background_pvalues": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64,

@@ -18,15 +18,15 @@
 // host enumerates it once per call) are summed by one thread each -- a leaf is 1 KB of
 // consecutive doubles, so a warp streams 32 leaves through L1 -- and thread 0 folds the leaf
 // sums with the tree's post-order program.
-#include <vector>
-
-#include "fp_common.cuh"
+#include "row_tree.cuh"
 
 namespace {
 
-struct Leaf {
-    int lo, n;
-};
+using fp::rowtree::Leaf;
+using fp::rowtree::fold_tree;
+using fp::rowtree::build_tree;
+using fp::rowtree::MAX_DEPTH;
+using fp::rowtree::align_up;
 
 struct RowLoad {
     const double *x;
@@ -41,23 +41,7 @@ struct RowSqDev {
     }
 };
 
-// post-order program: entry >= 0 pushes the sum of that leaf, -1 pops two and pushes their sum
-__device__ double fold_tree(const double *leaf_sum, const int *__restrict__ prog, int n_prog, double *stack) {
-    int sp = 0;
-    for (int p = 0; p < n_prog; ++p) {
-        const int op = prog[p];
-        if (op >= 0) {
-            stack[sp++] = leaf_sum[op];
-        } else {
-            const double b = stack[--sp], a = stack[--sp];
-            stack[sp++] = __dadd_rn(a, b);
-        }
-    }
-    return stack[0];
-}
-
 constexpr int ROW_THREADS = 256;
-constexpr int MAX_DEPTH = 48;
 
 __global__ void __launch_bounds__(ROW_THREADS)
 row_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out,
@@ -107,30 +91,11 @@ col_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double 
     for (long g = 0; g < G; ++g) out[g * ld_out + c] = __ddiv_rn(__dsub_rn(X[g * ld + c], mean), sd);
 }
 
-// NumPy's pairwise_sum recursion (numpy/_core/src/umath/loops_utils.h.src): n > 128 splits at
-// n/2 rounded down to a multiple of 8
-void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
-    if (depth > max_depth) max_depth = depth;
-    if (n <= 128) {
-        prog.push_back((int)leaves.size());
-        leaves.push_back(Leaf{(int)lo, (int)n});
-        return;
-    }
-    long n2 = n / 2;
-    n2 -= n2 % 8;
-    build_tree(lo, n2, leaves, prog, depth + 1, max_depth);
-    build_tree(lo + n2, n - n2, leaves, prog, depth + 1, max_depth);
-    prog.push_back(-1);
-}
-
-size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-
 }  // namespace
 
 extern "C" size_t fp_normalize_rows_workspace_bytes(int64_t N) {
     if (N <= 0) return 0;
-    const size_t max_leaves = (size_t)(N / 32 + 2);
-    return align_up(max_leaves * sizeof(Leaf)) + align_up(2 * max_leaves * sizeof(int)) + 256;
+    return fp::rowtree::workspace_bytes(N);
 }
 
 extern "C" int fp_normalize_rows(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,

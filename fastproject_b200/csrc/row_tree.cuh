@@ -1,0 +1,61 @@
+// NumPy's pairwise summation tree over one contiguous row, shared by the kernels that must
+// reproduce add.reduce(axis=1) bit for bit (normalize.cu, weights.cu).
+//
+// add.reduce along the contiguous axis sums blocks of <= 128 elements with eight interleaved
+// accumulators and combines halves recursively (numpy/_core/src/umath/loops_utils.h.src:
+// n > 128 splits at n/2 rounded down to a multiple of 8).  The tree depends on N only: the host
+// enumerates its leaves once per call; on the device one thread sums a leaf
+// (fp::np_pairwise_sum) and one thread folds the leaf sums with the tree's post-order program.
+#pragma once
+#include <vector>
+
+#include "fp_common.cuh"
+
+namespace fp {
+namespace rowtree {
+
+struct Leaf {
+    int lo, n;
+};
+
+constexpr int MAX_DEPTH = 48;
+
+// post-order program: entry >= 0 pushes the sum of that leaf, -1 pops two and pushes their sum
+__device__ inline double fold_tree(const double *leaf_sum, const int *__restrict__ prog, int n_prog, double *stack) {
+    int sp = 0;
+    for (int p = 0; p < n_prog; ++p) {
+        const int op = prog[p];
+        if (op >= 0) {
+            stack[sp++] = leaf_sum[op];
+        } else {
+            const double b = stack[--sp], a = stack[--sp];
+            stack[sp++] = __dadd_rn(a, b);
+        }
+    }
+    return stack[0];
+}
+
+inline void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
+    if (depth > max_depth) max_depth = depth;
+    if (n <= 128) {
+        prog.push_back((int)leaves.size());
+        leaves.push_back(Leaf{(int)lo, (int)n});
+        return;
+    }
+    long n2 = n / 2;
+    n2 -= n2 % 8;
+    build_tree(lo, n2, leaves, prog, depth + 1, max_depth);
+    build_tree(lo + n2, n - n2, leaves, prog, depth + 1, max_depth);
+    prog.push_back(-1);
+}
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// bytes of device workspace for the leaves + program of rows of N elements
+inline size_t workspace_bytes(long N) {
+    const size_t max_leaves = (size_t)(N / 32 + 2);
+    return align_up(max_leaves * sizeof(Leaf)) + align_up(2 * max_leaves * sizeof(int)) + 256;
+}
+
+}  // namespace rowtree
+}  // namespace fp

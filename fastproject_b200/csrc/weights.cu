@@ -1,0 +1,164 @@
+// False-negative weights of the expression matrix -- the producer of the W matrix that the
+// scoring kernels read.  Replaces
+// /root/reference/FastProject/Transforms.py:266-316 (compute_weights) with the logistic
+// false-negative curve of create_false_neg_map (:87-88) as fit function, and :341-381
+// (estimate_non_detection with DO_GMM = False: p_nd = [x == 0]) when no p_nd is passed.
+//
+//   p_d      = 1 - p_nd
+//   mu_g     = sum_n(x * p_d) / sum_n(p_d)                    (mean of the detected values)
+//   fn_gn    = L_n + S_n / (1 + exp((mu_g - x0_n) * a_n))     (false-negative rate)
+//   pd_e     = 1 - fn
+//   pnd_g    = mean_n(p_nd);  pe_g = (1 - pnd_g) / mean_n(pd_e);  pnd_g == 0 -> 1 / N
+//   pne_nd   = clip(1 - (1 - pd_e) * pe / pnd, 0, 1)
+//   W        = pne_nd * p_nd + p_d
+//
+// One CTA per gene, three sweeps over the row (the second and third hit L2): the row sums
+// follow NumPy's pairwise order (row_tree.cuh) and every operation is rounded separately in
+// the reference's order, so the only difference from the reference is the last-bit freedom of
+// exp() (CUDA's and NumPy's are both within 1 ulp but not identical): weights agree to
+// ~1e-15, tested at 1e-12.  NaN propagates as in the reference (a gene that is never
+// detected has mu = 0/0; the reference's line 305 compares instead of assigning).
+#include "row_tree.cuh"
+
+namespace {
+
+using fp::rowtree::Leaf;
+using fp::rowtree::fold_tree;
+using fp::rowtree::build_tree;
+using fp::rowtree::MAX_DEPTH;
+using fp::rowtree::align_up;
+
+constexpr int W_THREADS = 256;
+
+__device__ __forceinline__ double p_nd_at(const double *x, const double *pnd_row, long i) {
+    return pnd_row ? pnd_row[i] : (x[i] == 0.0 ? 1.0 : 0.0);
+}
+
+struct DetectedValue {       // x * p_d
+    const double *x, *pnd;
+    __device__ double operator()(long i) const { return __dmul_rn(x[i], __dsub_rn(1.0, p_nd_at(x, pnd, i))); }
+};
+struct Detected {            // p_d
+    const double *x, *pnd;
+    __device__ double operator()(long i) const { return __dsub_rn(1.0, p_nd_at(x, pnd, i)); }
+};
+struct NotDetected {         // p_nd
+    const double *x, *pnd;
+    __device__ double operator()(long i) const { return p_nd_at(x, pnd, i); }
+};
+
+__device__ __forceinline__ double fn_rate(double mu, const double *__restrict__ params, long ldp, long i) {
+    const double x0 = params[i], a = params[ldp + i], L = params[2 * ldp + i], S = params[3 * ldp + i];
+    const double e = exp(__dmul_rn(__dsub_rn(mu, x0), a));
+    return __dadd_rn(L, __ddiv_rn(S, __dadd_rn(1.0, e)));
+}
+struct ExpressedDetect {     // pd_e = 1 - fn
+    double mu;
+    const double *params;
+    long ldp;
+    __device__ double operator()(long i) const { return __dsub_rn(1.0, fn_rate(mu, params, ldp, i)); }
+};
+
+__global__ void __launch_bounds__(W_THREADS)
+compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ P_nd, const double *__restrict__ params,
+                       long ldp, long G, long N, long ld, long ld_pnd, double *__restrict__ out, long ld_out,
+                       const Leaf *__restrict__ leaves, int n_leaves, const int *__restrict__ prog, int n_prog) {
+    extern __shared__ double leaf_sum[];                 // 3 * n_leaves
+    __shared__ double stack[MAX_DEPTH];
+    __shared__ double stat[3];                           // mu, pe, pnd
+    double *sum_a = leaf_sum, *sum_b = leaf_sum + n_leaves, *sum_c = leaf_sum + 2 * n_leaves;
+    for (long g = blockIdx.x; g < G; g += gridDim.x) {
+        const double *row = X + g * ld;
+        const double *prow = P_nd ? P_nd + g * ld_pnd : nullptr;
+        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
+            sum_a[l] = fp::np_pairwise_sum(DetectedValue{row, prow}, leaves[l].lo, leaves[l].n);
+            sum_b[l] = fp::np_pairwise_sum(Detected{row, prow}, leaves[l].lo, leaves[l].n);
+            sum_c[l] = fp::np_pairwise_sum(NotDetected{row, prow}, leaves[l].lo, leaves[l].n);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double sxp = fold_tree(sum_a, prog, n_prog, stack);
+            const double sp = fold_tree(sum_b, prog, n_prog, stack);
+            const double snd = fold_tree(sum_c, prog, n_prog, stack);
+            stat[0] = __ddiv_rn(sxp, sp);
+            stat[2] = __ddiv_rn(snd, (double)N);
+        }
+        __syncthreads();
+        const double mu = stat[0];
+        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
+            sum_a[l] = fp::np_pairwise_sum(ExpressedDetect{mu, params, ldp}, leaves[l].lo, leaves[l].n);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double mean_pde = __ddiv_rn(fold_tree(sum_a, prog, n_prog, stack), (double)N);
+            double pnd = stat[2];
+            stat[1] = __ddiv_rn(__dsub_rn(1.0, pnd), mean_pde);
+            if (pnd == 0.0) pnd = __ddiv_rn(1.0, (double)N);       // "for stability" (:307)
+            stat[2] = pnd;
+        }
+        __syncthreads();
+        const double pe = stat[1], pnd = stat[2];
+        double *orow = out + g * ld_out;
+        for (long c = threadIdx.x; c < N; c += blockDim.x) {
+            const double p_nd = p_nd_at(row, prow, c);
+            const double p_d = __dsub_rn(1.0, p_nd);
+            const double pd_e = __dsub_rn(1.0, fn_rate(mu, params, ldp, c));
+            // 1 - (1 - pd_e) * pe / pnd, evaluated left to right
+            double v = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(__dsub_rn(1.0, pd_e), pe), pnd));
+            if (v < 0.0) v = 0.0;
+            if (v > 1.0) v = 1.0;
+            orow[c] = __dadd_rn(__dmul_rn(v, p_nd), p_d);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" size_t fp_compute_weights_workspace_bytes(int64_t N) {
+    if (N <= 0) return 0;
+    return fp::rowtree::workspace_bytes(N);
+}
+
+extern "C" int fp_compute_weights(const double *X, const double *p_nd, const double *params, int64_t G, int64_t N,
+                                  int64_t ld, int64_t ld_pnd, double *out_weights, int64_t ld_out, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(X && params && out_weights, "fp_compute_weights: null pointer");
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N && (!p_nd || ld_pnd >= N),
+                 "fp_compute_weights: bad shape G=%ld N=%ld", (long)G, (long)N);
+    FP_CHECK_ARG(N < (1L << 31), "fp_compute_weights: N too large");
+    std::vector<Leaf> leaves;
+    std::vector<int> prog;
+    int max_depth = 0;
+    build_tree(0, N, leaves, prog, 1, max_depth);
+    const size_t smem = 3 * leaves.size() * sizeof(double);
+    if (max_depth + 1 > MAX_DEPTH || smem > 200 * 1024) {
+        fp::set_error("fp_compute_weights: rows of %ld cells need %zu tree leaves (limit 8533)", (long)N,
+                      leaves.size());
+        return FP_EUNSUPPORTED;
+    }
+    const size_t leaves_b = align_up(leaves.size() * sizeof(Leaf)), prog_b = align_up(prog.size() * sizeof(int));
+    if (!workspace || workspace_bytes < leaves_b + prog_b) {
+        fp::set_error("fp_compute_weights: workspace %zu bytes < required %zu", workspace_bytes, leaves_b + prog_b);
+        return FP_EWORKSPACE;
+    }
+    cudaStream_t st = fp::as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    FP_CHECK_CUDA(cudaMemcpyAsync(ws, leaves.data(), leaves.size() * sizeof(Leaf), cudaMemcpyHostToDevice, st));
+    FP_CHECK_CUDA(cudaMemcpyAsync(ws + leaves_b, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    FP_CHECK_CUDA(cudaStreamSynchronize(st));          // the host vectors die at return
+    static size_t smem_set = 0;
+    if (smem > 40 * 1024 && smem > smem_set) {
+        FP_CHECK_CUDA(cudaFuncSetAttribute(compute_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        smem_set = smem;
+    }
+    long blocks = G;
+    const long cap = (long)fp::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    compute_weights_kernel<<<(unsigned)blocks, W_THREADS, smem, st>>>(
+        X, p_nd, params, N, G, N, ld, ld_pnd, out_weights, ld_out, reinterpret_cast<const Leaf *>(ws),
+        (int)leaves.size(), reinterpret_cast<const int *>(ws + leaves_b), (int)prog.size());
+    FP_CHECK_LAUNCH("compute_weights_kernel");
+    return FP_OK;
+}

@@ -134,6 +134,24 @@ int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, int64_t ld,
                        int method, void *stream);
 
 /*
+ * fp_compute_weights -- false-negative weights of the expression matrix, the W that
+ * fp_score_signatures reads.  Replaces Transforms.compute_weights (Transforms.py:266-316) for
+ * the logistic curve fn = L + S / (1 + exp((mu - x0) * a)) that create_false_neg_map (:87-88)
+ * fits per cell, and Transforms.estimate_non_detection (:341-381) when p_nd is NULL
+ * (p_nd = [x == 0]).
+ *   X       : G x N expression (row-major, leading dimension ld)
+ *   p_nd    : G x N probability of non-detection (leading dimension ld_pnd) or NULL
+ *   params  : 4 x N, rows x0, a, L, S (the reference's params matrix), contiguous
+ *   out     : G x N weights in [0, 1] (1 where detected); may not alias X
+ * Row sums in NumPy's pairwise order, operations in the reference's order; differs from the
+ * reference only by the last-bit freedom of exp() (tested at 1e-12).  NaN propagates as there.
+ */
+size_t fp_compute_weights_workspace_bytes(int64_t N);
+int fp_compute_weights(const double *X, const double *p_nd, const double *params, int64_t G, int64_t N,
+                       int64_t ld, int64_t ld_pnd, double *out_weights, int64_t ld_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/*
  * fp_pull_host -- copy `bytes` bytes from PINNED host memory (cudaHostAlloc / cudaHostRegister,
  * addressable by the device under unified addressing) to device memory with a kernel instead
  * of the copy engine.  For the small per-call tables of the path (signature CSR arrays of

@@ -466,6 +466,40 @@ def col_rank_normalization(data):
     return out
 
 
+def logistic_fnr(xvals, x0, a, L=0, S=1):
+    """Transforms.py:87-88 -- the false-negative-rate curve that create_false_neg_map fits per
+    cell and hands to compute_weights as ``fit_func``."""
+    return L + S / (1 + np.exp((xvals - x0) * a))
+
+
+def estimate_non_detection(data):
+    """Transforms.py:341-381 with DO_GMM = False (:358): probability of non-detection is the
+    zero mask."""
+    return (np.asarray(data) == 0).astype("float")
+
+
+def compute_weights(fit_func, params, data, p_nd):
+    """Transforms.py:266-316 -- weights p(not expressed | not detected) of the zero entries,
+    1.0 for detected values.  ``data``, ``p_nd``: genes x cells arrays; ``params``: 4 x cells."""
+    data = np.asarray(data, dtype=np.float64)
+    p_nd = np.array(p_nd, dtype=np.float64)
+    p_d = 1 - p_nd
+    with np.errstate(all="ignore"):
+        mu_h = (data * p_d).sum(axis=1) / p_d.sum(axis=1)
+        fn_prob = np.zeros(data.shape)
+        for i in range(fn_prob.shape[1]):
+            fn_prob[:, i] = fit_func(mu_h, *params[:, i]).ravel()
+        pd_e = 1 - fn_prob
+        pnd = p_nd.mean(axis=1, keepdims=True)
+        pe = (1 - pnd) / (pd_e).mean(axis=1, keepdims=True)
+        # (:305 of the reference compares instead of assigning: NaN stays NaN)
+        pnd[pnd == 0] = 1.0 / data.shape[1]
+        pne_nd = 1 - (1 - pd_e) * pe / pnd
+        pne_nd[pne_nd < 0] = 0.0
+        pne_nd[pne_nd > 1] = 1.0
+        return pne_nd * p_nd + p_d
+
+
 def normalize_projection(xy):
     """Projections.py:100-113 -- centre, scale 90th-percentile radius to 1.
     ``xy`` is (N,2); returns (2,N)."""

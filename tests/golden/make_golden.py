@@ -288,7 +288,52 @@ def norm_case():
     return out
 
 
+def weights_case():
+    """Transforms.compute_weights (:266-316) of the live reference with the logistic curve of
+    create_false_neg_map (:87-88; a closure there, restated here) and seeded per-cell
+    parameters; p_nd from Transforms.estimate_non_detection (:341-381)."""
+    import pandas as pd
+    from FastProject import Transforms as RefT
+
+    def func(xvals, x0, a, L=0, S=1):
+        return L + S / (1 + np.exp((xvals - x0) * a))
+
+    rng = np.random.RandomState((RANDOM_SEED + 7) % (2 ** 32))
+    out = dict(versions())
+    for tag, shape in (("small", (37, 53)), ("wide", (11, 1237))):
+        g, n = shape
+        x = np.log1p(rng.gamma(0.6, 5.0, size=shape)) * (rng.uniform(size=shape) < 0.55)
+        x[2, :] = 0.0                                   # never detected: mu_h = 0/0
+        x[4, :] = 1.0 + rng.uniform(size=n)             # always detected: pnd == 0 -> 1/N
+        x[6, :] = 0.0
+        x[6, 3] = 2.0                                   # detected once
+        genes = ["G%03d" % i for i in range(g)]
+        cells = ["c%04d" % i for i in range(n)]
+        params = np.zeros((4, n))
+        params[0] = rng.uniform(0.5, 4.0, size=n)
+        params[1] = rng.uniform(0.0, 2.0, size=n)
+        params[1, :3] = [0.0, 2.0, 1e-3]
+        params[2] = 0.0
+        params[3] = 1.0
+        if tag == "small":                              # general L, S as the signature allows
+            params[2, 10:20] = 0.05
+            params[3, 10:20] = 0.9
+        data = ExpressionData(x.copy(), genes, cells)
+        p_nd = RefT.estimate_non_detection(pd.DataFrame(x, index=genes, columns=cells))
+        with np.errstate(all="ignore"):
+            w = RefT.compute_weights(func, params, data, p_nd)
+        out[tag + "_X"] = x
+        out[tag + "_params"] = params
+        out[tag + "_p_nd"] = p_nd.values
+        out[tag + "_weights"] = w
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "weights":
+        np.savez_compressed(os.path.join(HERE, "case_weights.npz"), **weights_case())
+        return
+    np.savez_compressed(os.path.join(HERE, "case_weights.npz"), **weights_case())
     np.savez_compressed(os.path.join(HERE, "case_norm.npz"), **norm_case())
     np.savez_compressed(os.path.join(HERE, "case_synth_odd.npz"),
                         **synth_case(240, 65, 3, 1001, True, False))

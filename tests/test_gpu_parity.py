@@ -516,6 +516,62 @@ def test_normalization_midsize_bit_exact_vs_oracle_and_device_path(fp):
     assert np.array_equal(got["s"].scores, want["s"].scores)
 
 
+# ------------------------------------------------------------------ false-negative weights (next row N3)
+WEIGHT_TOL = 1e-12      # absolute, weights in [0, 1]: exp() of CUDA and of NumPy differ in the last bit
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_compute_weights_vs_reference_golden(fp, tag):
+    from fastproject_b200 import Transforms as T
+    c = G.load("case_weights")
+    x, params, want = c[tag + "_X"], c[tag + "_params"], c[tag + "_weights"]
+    got = T.compute_weights(T.logistic_fnr, params, x)                 # p_nd = zero mask on the device
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got, want, rtol=0, atol=WEIGHT_TOL, equal_nan=True)
+    assert (got[x != 0] == 1.0).all()                                  # detected values: exactly 1
+    # explicit p_nd (array and DataFrame selected by the data's labels, like the reference)
+    import pandas as pd
+    got2 = T.compute_weights(None, params, x, T.estimate_non_detection(x))
+    assert np.array_equal(got2, got, equal_nan=True)
+    genes = ["G%03d" % i for i in range(x.shape[0])]
+    cells = ["c%04d" % i for i in range(x.shape[1])]
+    df = T.estimate_non_detection(pd.DataFrame(x, index=genes, columns=cells))
+    data = fp.synth.ExpressionMatrix(x, x * 0 + 1, genes, cells)
+    shuffled = df.iloc[::-1, ::-1]                                     # label-based selection restores the order
+    got3 = T.compute_weights(lambda v, x0, a, L=0, S=1: L + S / (1 + np.exp((v - x0) * a)), params, data, shuffled)
+    assert np.array_equal(got3, got, equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        T.compute_weights(lambda v, x0, a, L=0, S=1: np.tanh(v), params, x)
+
+
+def test_compute_weights_midsize_vs_oracle_and_feeds_scoring(fp):
+    """20 000 cells per gene, soft p_nd, device-resident output feeding calculate_sig_scores."""
+    import torch
+    from fastproject_b200 import Transforms as T
+    rng = np.random.RandomState(9)
+    g, n = 48, 20000
+    x = np.log1p(rng.gamma(0.6, 5.0, size=(g, n))) * (rng.uniform(size=(g, n)) < 0.5)
+    params = np.vstack([rng.uniform(0.5, 4.0, size=n), rng.uniform(0.0, 2.0, size=n), np.zeros(n), np.ones(n)])
+    want = O.compute_weights(O.logistic_fnr, params, x, O.estimate_non_detection(x))
+    got = T.compute_weights(T.logistic_fnr, params, x)
+    np.testing.assert_allclose(got, want, rtol=0, atol=WEIGHT_TOL)
+    soft = np.clip(O.estimate_non_detection(x) * 0.9 + 0.05 * rng.uniform(size=(g, n)), 0, 1)
+    want = O.compute_weights(O.logistic_fnr, params, x, soft)
+    np.testing.assert_allclose(T.compute_weights(None, params, x, soft), want, rtol=0, atol=WEIGHT_TOL)
+    w_dev = T.compute_weights(None, torch.from_numpy(params).cuda(), torch.from_numpy(x).cuda())
+    assert w_dev.is_cuda
+    np.testing.assert_allclose(w_dev.cpu().numpy(), O.compute_weights(
+        O.logistic_fnr, params, x, O.estimate_non_detection(x)), rtol=0, atol=WEIGHT_TOL)
+    genes = ["g%d" % i for i in range(g)]
+    cells = ["c%d" % i for i in range(n)]
+    sig = fp.S.Signature(dict((q, 1) for q in genes[:20]), False, "t", "s")
+    res = fp.S.calculate_sig_scores(fp.synth.ExpressionMatrix(torch.from_numpy(x).cuda(), w_dev, genes, cells),
+                                    [sig], "weighted_avg", None, 5)
+    ref = O.calculate_sig_scores(O.ExpressionMatrix(x, w_dev.cpu().numpy(), genes, cells),
+                                 [O.Signature(sig.sig_dict, False, "t", "s")], "weighted_avg", None, 5)
+    assert np.array_equal(res["s"].scores, ref["s"].scores)
+
+
 # ------------------------------------------------------------------ Interactive wrappers (next row N4)
 def test_interactive_dataframe_wrappers_vs_oracle(fp):
     import pandas as pd

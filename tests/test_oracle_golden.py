@@ -119,3 +119,16 @@ def test_normalization_methods_bit_exact(tag):
     assert np.array_equal(O.col_normalization(x.copy()), c[tag + "_cols"])
     assert np.array_equal(O.row_and_col_normalization(x.copy()), c[tag + "_rows_cols"])
     assert np.array_equal(O.col_rank_normalization(x.copy()), c[tag + "_col_rank"])
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_compute_weights_bit_exact(tag):
+    """Oracle restatement of Transforms.compute_weights / estimate_non_detection against the
+    live reference (never-detected gene -> NaN row, always-detected gene, general L and S)."""
+    c = G.load("case_weights")
+    x = c[tag + "_X"]
+    p_nd = O.estimate_non_detection(x)
+    assert np.array_equal(p_nd, c[tag + "_p_nd"])
+    w = O.compute_weights(O.logistic_fnr, c[tag + "_params"], x, p_nd)
+    assert np.array_equal(w, c[tag + "_weights"], equal_nan=True)
+    assert np.isnan(w[2]).all() and (w[4] == 1.0).all()
