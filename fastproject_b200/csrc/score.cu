@@ -17,27 +17,71 @@ namespace {
 // contiguous bytes of a gene row (two full 128-byte lines) per operand.
 // Launch order: blockIdx.x runs over the signature tiles of ONE slab of 32
 // cells, blockIdx.y over the slabs, so the CTAs in flight all gather from the
-// same G x 32-cell slab of X and W (7.7 MB at G = 15 000): it is read from HBM
-// once and served from L2 to the ~15 signatures that touch each gene row.
+// same few G x 32-cell slabs of X and W (7.7 MB each at G = 15 000), which are
+// served from L2 to the ~15 signatures that touch each gene row.
 // (Round-1 profile of the transposed order: 73.9 GB of DRAM reads for 4.8 GB of
 // input, L2 hit rate 0.7 %.)
-constexpr int kCellsPerBlock = 32;    // blockDim.x: one warp wide -> slab of G x 32 cells (7.7 MB of X+W at G = 15 000)
+//
+// Memory-level parallelism: a thread first loads the indices of kDepth genes,
+// then all their operands, and only then accumulates -- in ascending gene
+// order, every operation separately rounded, exactly as a one-gene-at-a-time
+// loop would (bit-identical results).  The first version issued the loads of
+// one gene, waited, accumulated, and only then addressed the next gene
+// (volatile loads, 32 registers per thread): ~1 300 clk per gene and warp,
+// latency bound at 7 TB/s of L2 gather; eight genes in flight at 64 registers
+// and 1 024 threads per SM reach 13 TB/s, the L2 -> SM limit of the part
+// (8.5 -> 4.7 ms at 3 000 signatures x 20 000 cells, tests/cuda/score_profile.py).
+constexpr int kCellsPerBlock = 32;    // blockDim.x: one warp wide -> slab of G x 32 cells
 constexpr int kSigsPerBlock = 16;     // blockDim.y
+constexpr int kDepth = 8;             // genes in flight per thread
+constexpr int kMinBlocks = 2;         // CTAs per SM the register budget is set for (64 registers)
 
 __device__ __forceinline__ double ldg_stream(const double *p) {
-    // read-only, keep out of L1 (each value is used once by this thread)
+    // read-only, keep out of L1 (each value is used once by this thread); not volatile, so
+    // the compiler may hoist the loads of later genes above the arithmetic of earlier ones
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 
+// one gene's contribution, the reference's operation order
 template <int METHOD>
-__global__ void __launch_bounds__(kCellsPerBlock *kSigsPerBlock)
+__device__ __forceinline__ void accumulate(double x, double w, double z, double mu, double s, double &num,
+                                           double &den, double &aux) {
+    if (METHOD == FP_METHOD_NAIVE) {
+        // pdata = data * sig * ones ; norm = |sig| * ones   (:38-41)
+        num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), 1.0));
+        den = __dadd_rn(den, 1.0);
+    } else if (METHOD == FP_METHOD_WEIGHTED) {
+        // pdata = data * sig * weights ; norm = |sig| * weights   (:70-73)
+        num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), w));
+        den = __dadd_rn(den, w);
+    } else if (METHOD == FP_METHOD_NONZERO) {
+        // (data * not_zeros) * sig ; norm = sum(not_zeros)   (:152-153)
+        const double nz = __dsub_rn(1.0, z);
+        num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
+        den = __dadd_rn(den, nz);
+    } else {  // FP_METHOD_IMPUTED (:105-121)
+        const double nz = __dsub_rn(1.0, z);
+        num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
+        const double t1 = __dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, w), mu), s), z);
+        const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(w, x), s), z);
+        aux = __dadd_rn(aux, __dadd_rn(t1, t2));
+    }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kCellsPerBlock *kSigsPerBlock, kMinBlocks)
 score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
                     const double *__restrict__ Z, long N, long ld,
                     const int32_t *__restrict__ sig_ptr, const int32_t *__restrict__ sig_gene,
                     const int8_t *__restrict__ sig_sign, long K,
                     const double *__restrict__ gene_mu, double *__restrict__ out, long ld_out) {
+    constexpr bool kUseW = METHOD == FP_METHOD_WEIGHTED || METHOD == FP_METHOD_IMPUTED;
+    constexpr bool kUseZ = METHOD == FP_METHOD_NONZERO || METHOD == FP_METHOD_IMPUTED;
+    constexpr bool kUseMu = METHOD == FP_METHOD_IMPUTED;
+    // the imputed method carries three operands + mu per gene: half the depth keeps it in registers
+    constexpr int D = METHOD == FP_METHOD_IMPUTED ? kDepth / 2 : kDepth;
     for (long slab = blockIdx.y; slab * kCellsPerBlock < N; slab += gridDim.y) {
     const long cell = slab * kCellsPerBlock + threadIdx.x;
     const bool live = cell < N;
@@ -46,34 +90,34 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
          k += (long)gridDim.x * kSigsPerBlock) {
         const int beg = sig_ptr[k], end = sig_ptr[k + 1];
         double num = 0.0, den = 0.0, aux = 0.0;
-        for (int t = beg; t < end; ++t) {
-            const long g = sig_gene[t];
-            const double s = (double)sig_sign[t];
-            const double x = ldg_stream(X + g * ld + c);
-            if (METHOD == FP_METHOD_NAIVE) {
-                // pdata = data * sig * ones ; norm = |sig| * ones   (:38-41)
-                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), 1.0));
-                den = __dadd_rn(den, 1.0);
-            } else if (METHOD == FP_METHOD_WEIGHTED) {
-                // pdata = data * sig * weights ; norm = |sig| * weights   (:70-73)
-                const double w = ldg_stream(W + g * ld + c);
-                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, s), w));
-                den = __dadd_rn(den, w);
-            } else if (METHOD == FP_METHOD_NONZERO) {
-                // (data * not_zeros) * sig ; norm = sum(not_zeros)   (:152-153)
-                const double nz = __dsub_rn(1.0, ldg_stream(Z + g * ld + c));
-                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
-                den = __dadd_rn(den, nz);
-            } else {  // FP_METHOD_IMPUTED (:105-121)
-                const double w = ldg_stream(W + g * ld + c);
-                const double z = ldg_stream(Z + g * ld + c);
-                const double nz = __dsub_rn(1.0, z);
-                const double mu = gene_mu[g];
-                num = __dadd_rn(num, __dmul_rn(__dmul_rn(x, nz), s));
-                const double t1 = __dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, w), mu), s), z);
-                const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(w, x), s), z);
-                aux = __dadd_rn(aux, __dadd_rn(t1, t2));
+        int t = beg;
+        for (; t + D <= end; t += D) {
+            int g[D];
+            double x[D], w[D], z[D], mu[D], s[D];
+#pragma unroll
+            for (int e = 0; e < D; ++e) g[e] = sig_gene[t + e];
+#pragma unroll
+            for (int e = 0; e < D; ++e) {
+                const long o = (long)g[e] * ld + c;
+                x[e] = ldg_stream(X + o);
+                w[e] = kUseW ? ldg_stream(W + o) : 0.0;
+                z[e] = kUseZ ? ldg_stream(Z + o) : 0.0;
             }
+#pragma unroll
+            for (int e = 0; e < D; ++e) {
+                s[e] = (double)sig_sign[t + e];
+                mu[e] = kUseMu ? gene_mu[g[e]] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < D; ++e) accumulate<METHOD>(x[e], w[e], z[e], mu[e], s[e], num, den, aux);
+        }
+        for (; t < end; ++t) {
+            const int g = sig_gene[t];
+            const long o = (long)g * ld + c;
+            const double x = ldg_stream(X + o);
+            const double w = kUseW ? ldg_stream(W + o) : 0.0;
+            const double z = kUseZ ? ldg_stream(Z + o) : 0.0;
+            accumulate<METHOD>(x, w, z, kUseMu ? gene_mu[g] : 0.0, (double)sig_sign[t], num, den, aux);
         }
         double score;
         if (METHOD == FP_METHOD_NAIVE) {

@@ -20,3 +20,22 @@ xh = x[:2000].cpu().numpy()
 t0 = time.perf_counter()
 mu = xh.mean(axis=1, keepdims=True); sd = xh.std(axis=1, keepdims=True); sd[sd == 0] = 1; y = (xh - mu) / sd
 print("numpy row_normalization on 2000 of the rows: %.1f ms -> %.0f ms for all" % ((time.perf_counter() - t0) * 1e3, (time.perf_counter() - t0) * 1e3 * G / 2000))
+# false-negative weights (fp_compute_weights) at the same shape
+xe = torch.where(torch.rand((G, N), device="cuda") < 0.5, torch.zeros_like(x), x.abs())
+params = torch.stack([torch.rand(N, dtype=torch.float64, device="cuda") * 3 + 0.5,
+                      torch.rand(N, dtype=torch.float64, device="cuda") * 2,
+                      torch.zeros(N, dtype=torch.float64, device="cuda"),
+                      torch.ones(N, dtype=torch.float64, device="cuda")])
+E.compute_weights(xe, params); torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ev[0].record()
+for r in range(2):
+    E.compute_weights(xe, params); ev[r + 1].record()
+torch.cuda.synchronize()
+ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(2))
+print("compute_weights %dx%d: %.2f ms  (%.0f GB/s of 1 read + 1 write)" % (G, N, ms, G * N * 8 * 2 / ms / 1e6))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import fp_oracle as O
+xh = xe[:300].cpu().numpy(); ph = params.cpu().numpy()
+t0 = time.perf_counter(); O.compute_weights(O.logistic_fnr, ph, xh, O.estimate_non_detection(xh)); dt = time.perf_counter() - t0
+print("numpy compute_weights on 300 of the rows: %.0f ms -> %.1f s for all" % (dt * 1e3, dt * G / 300))
