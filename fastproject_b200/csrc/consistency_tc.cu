@@ -380,8 +380,9 @@ template <int SR>
 struct MmaSmem {
     static constexpr int stages = SR == 2 ? 3 : 2;
     static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
-    static constexpr int den_off = stages * stage_bytes;
-    static constexpr int bar_off = den_off + TN * 8;
+    static constexpr int den_off = stages * stage_bytes;     // sum_j W_ij per column, then its scaled reciprocal
+    static constexpr int rden_off = den_off + TN * 8;
+    static constexpr int bar_off = rden_off + TN * 8;
     static constexpr int total = bar_off + 256;
 };
 
@@ -401,6 +402,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
     double *den_s = reinterpret_cast<double *>(smem + L::den_off);
+    double *rden_s = reinterpret_cast<double *>(smem + L::rden_off);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES] leader's are used
     uint64_t *empty = full + 4;                                                  // [STAGES] one per CTA
     uint64_t *accum_full = empty + 4;                                            // one per CTA
@@ -528,6 +530,15 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
             const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
             const bool invalid = *flag != 0;
+            if (last) {
+                // one division per column instead of one per output; zero row sum -> prediction 0
+                // (Signatures.py:400-402)
+                if (tid - 64 < TN) {
+                    const double den = den_s[tid - 64];
+                    rden_s[tid - 64] = den > 0.0 ? inv_scale / den : __longlong_as_double(0x7ff8000000000000LL);
+                }
+                named_barrier_sync(1, EPI_THREADS);
+            }
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {
                 const int col0 = part * 32 + b * 16;
@@ -552,10 +563,9 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                             orow[e] = total;
                             continue;
                         }
-                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2;
-                        // zero row sum -> prediction 0 (Signatures.py:400-402)
-                        const double den = den_s[col0 + e];
-                        double r = den > 0.0 ? 0.5 * ((total / den) * inv_scale + centre) : 0.0;
+                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2
+                        const double rden = rden_s[col0 + e];
+                        double r = rden == rden ? 0.5 * (total * rden + centre) : 0.0;
                         if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
                         if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
                         orow[e] = r;
