@@ -136,8 +136,12 @@ def _device_rank_rows(score_objs, n_cells):
             host_rows.append(pos)
     for batch, dst, src in by_batch.values():
         ranks = batch.ranks_dev()
-        d = torch.as_tensor(dst, device=dev, dtype=torch.long)
-        s = torch.as_tensor(src, device=dev, dtype=torch.long)
+        if dst == list(range(dst[0], dst[0] + len(dst))) and src == list(range(src[0], src[0] + len(src))):
+            out[dst[0]:dst[0] + len(dst)] = ranks[src[0]:src[0] + len(src)]     # whole batches in order
+            continue
+        # (index tables go through _engine.to_device: not a copy-engine transfer)
+        d = _engine.to_device(np.asarray(dst, dtype=np.int64), torch.long)
+        s = _engine.to_device(np.asarray(src, dtype=np.int64), torch.long)
         out.index_copy_(0, d, ranks.index_select(0, s))
     if host_rows:
         need_rank = [p for p in host_rows if getattr(score_objs[p], "_ranks", None) is None]
@@ -146,7 +150,7 @@ def _device_rank_rows(score_objs, n_cells):
             for r, p in enumerate(need_rank):
                 mat[r, :n_cells] = np.asarray(score_objs[p].scores, dtype=np.float64)
             ranked = _engine.rank_rows(_engine.to_device(mat), n_cells)
-            out.index_copy_(0, torch.as_tensor(need_rank, device=dev, dtype=torch.long), ranked)
+            out.index_copy_(0, _engine.to_device(np.asarray(need_rank, dtype=np.int64), torch.long), ranked)
             host = ranked[:, :n_cells].cpu().numpy()
             for r, p in enumerate(need_rank):
                 score_objs[p]._ranks = host[r]
@@ -155,7 +159,7 @@ def _device_rank_rows(score_objs, n_cells):
             mat = np.zeros((len(have), ld), dtype=np.float64)
             for r, p in enumerate(have):
                 mat[r, :n_cells] = score_objs[p]._ranks
-            out.index_copy_(0, torch.as_tensor(have, device=dev, dtype=torch.long),
+            out.index_copy_(0, _engine.to_device(np.asarray(have, dtype=np.int64), torch.long),
                             _engine.to_device(mat))
     return out
 
@@ -362,7 +366,7 @@ def _single_group_pvalue(med_value, bg_medians):
     dev = bg_medians.device
     n = bg_medians.shape[0]
     order = torch.arange(n, dtype=torch.int32, device=dev)
-    gptr = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    gptr = _engine.to_device(np.array([0, n], dtype=np.int32), torch.int32)
     grp = torch.zeros((1,), dtype=torch.int32, device=dev)
     p, mu, sd = _engine.background_pvalues(med_value.reshape(1), grp, bg_medians, order, gptr)
     return float(p[0]), float(sd[0])

@@ -60,15 +60,23 @@ def all_gather_rows(local, n_rows_total=None, group=None):
     return out
 
 
+def _small_to(arr, device):
+    """Small host table -> tensor on ``device``; on CUDA through the engine's kernel fetch, so
+    that it does not queue behind a large upload on the copy engine."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if device is None or torch.device(device).type != "cuda":
+        return t if device is None else t.to(device)
+    from . import _engine
+    return _engine.to_device(np.ascontiguousarray(arr), t.dtype)
+
+
 def all_gather_counts(counts, group=None, device=None):
     """numGenes of every rank's rows, rank-major (host int64 array)."""
     world_size, rank = world()
     counts = np.asarray(counts, dtype=np.int64)
     if world_size == 1:
         return counts
-    t = torch.from_numpy(counts.reshape(1, -1).copy())
-    if device is not None:
-        t = t.to(device)
+    t = _small_to(counts.reshape(1, -1).copy(), device)
     return all_gather_rows(t, group=group)[0].cpu().numpy()
 
 
@@ -98,11 +106,11 @@ class GlobalBackground(object):
         self.order_host, self.gptr_host, self.grp_host = order, gptr, grp
         self.device = device
         if device is not None and torch.device(device).type == "cuda":
-            self.real_cols = torch.from_numpy(self.real_cols_host).to(device)
-            self.rnd_cols = torch.from_numpy(self.rnd_cols_host).to(device)
-            self.order = torch.from_numpy(order).to(device)
-            self.gptr = torch.from_numpy(gptr).to(device)
-            self.grp = torch.from_numpy(grp).to(device)
+            self.real_cols = _small_to(self.real_cols_host, device)
+            self.rnd_cols = _small_to(self.rnd_cols_host, device)
+            self.order = _small_to(order, device)
+            self.gptr = _small_to(gptr, device)
+            self.grp = _small_to(grp, device)
 
     def pvalues(self, all_med):
         """all_med: [P x rows_total] CUDA float64 (gathered) -> [P x K_total]
