@@ -441,17 +441,25 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * L::stage_bytes);
+                // (FP_TC_DBG bits 2 / 4: timing experiments that leave out the weight / value loads)
+                const bool load_a = !(dbg & 4), load_b = !(dbg & 2);
+                if (rank == 0)
+                    mbar_arrive_expect_tx(&full[s], 2 * ((load_a ? SR * A_PLANE_BYTES : 0) +
+                                                         (load_b ? WD * B_PLANE_BYTES : 0)));
                 const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
                 uint8_t *dst = smem + s * L::stage_bytes;
+                if (load_a) {
 #pragma unroll
-                for (int b = 0; b < SR; ++b)
-                    tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS, (int)(b * Kpad + blk * TM),
-                                     leader_full);
+                    for (int b = 0; b < SR; ++b)
+                        tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS,
+                                         (int)(b * Kpad + blk * TM), leader_full);
+                }
+                if (load_b) {
 #pragma unroll
-                for (int a = 0; a < WD; ++a)
-                    tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
-                                     (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+                    for (int a = 0; a < WD; ++a)
+                        tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
+                                         (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+                }
             }
         }
         __syncwarp();
