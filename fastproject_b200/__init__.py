@@ -12,7 +12,8 @@ ABI of ``include/fastproject_b200.h``; there is no CPU fallback.
 from . import Global  # noqa: F401  (seeds the global ``random`` stream like the reference)
 
 __version__ = "0.1.0"
-__all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Transforms", "Interactive", "Global", "synth"]
+__all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Transforms", "Interactive", "FileIO",
+           "Pipelines", "Global", "synth"]
 
 
 def prefetch(*arrays, **kw):
@@ -25,8 +26,8 @@ def prefetch(*arrays, **kw):
 
 def __getattr__(name):
     # SigScoreMethods / Signatures import torch; keep ``import fastproject_b200`` light
-    if name in ("SigScoreMethods", "Signatures", "NormalizationMethods", "Transforms", "Interactive", "synth",
-                "distributed"):
+    if name in ("SigScoreMethods", "Signatures", "NormalizationMethods", "Transforms", "Interactive", "FileIO",
+                "Pipelines", "synth", "distributed"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

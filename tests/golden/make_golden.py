@@ -329,7 +329,47 @@ def weights_case():
     return out
 
 
+def writers_case():
+    """FileIO.write_matrix (:154-163) and write_signature_scores (:188-201) of the live reference
+    on awkward numbers (trailing zeros, negative zero, tiny, huge, nan, inf, half-way cases)."""
+    import tempfile
+    from FastProject import FileIO as RefIO
+    rng = np.random.RandomState((RANDOM_SEED + 11) % (2 ** 32))
+    special = np.array([0.0, -0.0, 1.0, -1.0, 10.0, 100.0, 1000000.0, 0.5, 0.00001, 0.000004, 0.000005,
+                        -0.000004, np.nan, np.inf, -np.inf, 1e20, 123456.789, 99.999996, 0.1 + 0.2, 1e-300,
+                        5e-6, 1.5e-5, 100.000001, 10.1, 1010.0, 0.100001, 2.5e-6, 0.000015])
+    vals = np.concatenate([rng.normal(size=272) * 10.0 ** rng.randint(-7, 8, size=272), special])
+    data = vals.reshape(12, 25)
+    rows = ["sig %d" % i for i in range(12)]
+    cols = ["proj%d" % i for i in range(25)]
+    tmp = tempfile.mkdtemp()
+    RefIO.write_matrix(os.path.join(tmp, "m.txt"), data, rows, cols)
+    scores = dict()
+    order = []
+    for i in range(5):
+        name = "S%d" % i
+        order.append(name)
+        scores[name] = RefSSM.SignatureScores(list(data[i]), name, cols, isFactor=False, isPrecomputed=False,
+                                              numGenes=3)
+    scores["F"] = RefSSM.SignatureScores(["a", "b", "c", "a", "b"] * 5, "F", cols, isFactor=True,
+                                         isPrecomputed=True, numGenes=0)
+    order.append("F")
+    RefIO.write_signature_scores(os.path.join(tmp, "s.txt"), scores, cols)
+    out = dict(versions())
+    out["data"] = data
+    out["rows"] = np.array(rows, dtype=str)
+    out["cols"] = np.array(cols, dtype=str)
+    out["score_order"] = np.array(order, dtype=str)
+    out["matrix_text"] = np.array(open(os.path.join(tmp, "m.txt")).read())
+    out["scores_text"] = np.array(open(os.path.join(tmp, "s.txt")).read())
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "writers":
+        np.savez_compressed(os.path.join(HERE, "case_writers.npz"), **writers_case())
+        return
+    np.savez_compressed(os.path.join(HERE, "case_writers.npz"), **writers_case())
     if len(sys.argv) > 1 and sys.argv[1] == "weights":
         np.savez_compressed(os.path.join(HERE, "case_weights.npz"), **weights_case())
         return

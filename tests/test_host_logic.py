@@ -105,3 +105,65 @@ def test_import_seeds_global_random_like_reference():
     first = random.random()
     random.seed(1335607828)
     assert first == random.random()
+
+
+def test_result_writers_byte_identical_to_reference(tmp_path):
+    """fastproject_b200.FileIO against text written by the live reference's FileIO.write_matrix /
+    write_signature_scores (tests/golden/make_golden.py writers_case)."""
+    from fastproject_b200 import FileIO
+    c = G.load("case_writers")
+    data, rows, cols = c["data"], [str(r) for r in c["rows"]], [str(x) for x in c["cols"]]
+    FileIO.write_matrix(str(tmp_path / "m.txt"), data, rows, cols)
+    assert open(str(tmp_path / "m.txt")).read() == str(c["matrix_text"])
+
+    class Scores(object):
+        def __init__(self, scores, is_factor):
+            self.scores, self.isFactor = scores, is_factor
+    sigs = dict()
+    for i, name in enumerate(str(n) for n in c["score_order"]):
+        sigs[name] = Scores(["a", "b", "c", "a", "b"] * 5, True) if name == "F" else Scores(data[i], False)
+    FileIO.write_signature_scores(str(tmp_path / "s.txt"), sigs, cols)
+    assert open(str(tmp_path / "s.txt")).read() == str(c["scores_text"])
+    FileIO.write_path_results(str(tmp_path / "out"), sigs, cols, data, data, rows, cols)
+    assert open(str(tmp_path / "out" / "PMatrix.txt")).read() == str(c["matrix_text"])
+    assert open(str(tmp_path / "out" / "SignatureScores.txt")).read() == str(c["scores_text"])
+
+
+def test_significance_filter_semantics():
+    """Pipelines.filter_significant_signatures (restatement of Pipelines.py:299-349; unpinned: the
+    reference block does not run on this pandas).  Checks the rules the block states."""
+    from fastproject_b200 import Pipelines as P
+
+    class Scores(object):
+        def __init__(self, pre):
+            self.isPrecomputed = pre
+    rng = np.random.RandomState(4)
+    keys = ["sig%03d" % i for i in rng.permutation(300)]
+
+    def model(scale):
+        def proj():
+            return dict(sigProjMatrix=rng.normal(size=(300, 4)),
+                        sigProjMatrix_p=-np.abs(rng.normal(size=(300, 4))) * scale, signatureKeys=list(keys))
+        return dict(signatureScores=dict((k, Scores(i % 50 == 0)) for i, k in enumerate(keys)),
+                    projectionData=[proj(), proj()])
+    # few samples, many significant: everything with min log10 q <= -1.3 stays (+ precomputed)
+    m = model(3.0)
+    names, vals = P.signature_significance(m["projectionData"])
+    assert names == sorted(keys)
+    want = set(k for k, v in zip(names, vals) if v <= -1.3) | set(k for k in keys if m["signatureScores"][k].isPrecomputed)
+    keep = P.filter_significant_signatures(m, n_samples=500)
+    assert set(k for k in keep if keep[k]) == want and len(want) > 200
+    for pd_ in m["projectionData"]:
+        assert pd_["signatureKeys"] == [k for k in keys if k in want]
+        assert pd_["sigProjMatrix"].shape == (len(want), 4) == pd_["sigProjMatrix_p"].shape
+    # few significant: the threshold rises to the 200th best value
+    m = model(0.2)
+    keep = P.filter_significant_signatures(m, n_samples=500)
+    n_kept_scored = sum(1 for k in keep if keep[k] and not m["signatureScores"][k].isPrecomputed)
+    assert 194 <= n_kept_scored <= 200
+    # many samples: hard limit of 200; all_sigs keeps everything
+    m = model(3.0)
+    keep = P.filter_significant_signatures(m, n_samples=5000)
+    assert sum(1 for k in keep if keep[k] and not m["signatureScores"][k].isPrecomputed) <= 200
+    m = model(3.0)
+    assert all(P.filter_significant_signatures(m, n_samples=5000, all_sigs=True).values())
