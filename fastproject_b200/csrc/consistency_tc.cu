@@ -118,7 +118,12 @@ nearest_neighbour_kernel(const double *__restrict__ coords, long N, unsigned lon
 __global__ void __launch_bounds__(256)
 cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ sigma_sq,
                   double sigma_sq_scalar, long N, long Npad, const unsigned long long *__restrict__ nn,
-                  CellI *__restrict__ ci, CellJ *__restrict__ cj) {
+                  CellI *__restrict__ ci, CellJ *__restrict__ cj, double *__restrict__ table) {
+    // 2^(k/128) * (2^32 - 1), 16 interleaved copies: every CTA of weight_planes_kernel copies it
+    // into shared memory instead of evaluating 2 048 exp2 of its own
+    if (blockIdx.x == 0)
+        for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += 256)
+            table[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
     if (i >= Npad) return;
     const double *cx = coords, *cy = coords + N;
@@ -322,16 +327,15 @@ __device__ __forceinline__ void issue_k_step(uint32_t tmem, uint64_t a_desc0, ui
 // ---------------------------------------------------------------------------
 constexpr int WG_THREADS = 256;
 constexpr int WG_COLS = 8;                 // cells j per thread: one 8-byte store per digit plane
-constexpr int WG_ROWS = 32;                // cells i per CTA
+constexpr int WG_ROWS = 64;                // cells i per CTA
 
 // planes[a][i - i_first][j] = digit a (0 = most significant) of W_ij; rows of Npad bytes
-__global__ void __launch_bounds__(WG_THREADS)
-weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj, long i_first, long slab_rows,
-                     long plane_rows, long Npad, uint8_t *__restrict__ planes) {
+__global__ void __launch_bounds__(WG_THREADS, 3)
+weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj, const double *__restrict__ table,
+                     long i_first, long slab_rows, long plane_rows, long Npad, uint8_t *__restrict__ planes) {
     __shared__ __align__(16) double tab[TAB * TAB_COPIES];
     __shared__ CellI rows_s[WG_ROWS];
-    for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += WG_THREADS)
-        tab[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
+    for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += WG_THREADS) tab[idx] = table[idx];
     const long r0 = (long)blockIdx.y * WG_ROWS;                   // slab-relative first row
     if (threadIdx.x < WG_ROWS) rows_s[threadIdx.x] = ci[i_first + r0 + threadIdx.x];
     __syncthreads();
@@ -616,7 +620,7 @@ struct Plan {
     int sr;
     long nblk, Kpad, Npad;
     long slab_tiles;                             // cell tiles (128 cells i) whose weight planes are resident at once
-    size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, weights_off, total;
+    size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, table_off, weights_off, total;
 };
 
 constexpr size_t kWeightSlabBudget = 6ull << 30;   // bytes of generated weight planes kept at a time
@@ -671,6 +675,8 @@ bool make_plan(long N, long K, Plan *p) {
     p->flag_off = off;
     p->range_off = off + 64;
     off += 1024;
+    p->table_off = off;
+    off += align_up((size_t)TAB * TAB_COPIES * 8, 1024);
     p->slab_tiles = pick_slab_tiles(p->Npad / TN, p->nblk / 2, p->Npad);
     p->weights_off = off;
     off += align_up((size_t)WD * p->slab_tiles * TN * p->Npad, 1024);
@@ -743,7 +749,8 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         nearest_neighbour_kernel<<<dim3(bx, by), 256, 0, st>>>(coords, N, nn);
         FP_CHECK_LAUNCH("nearest_neighbour_kernel");
         cell_setup_kernel<<<(unsigned)((p.Npad + 255) / 256), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N,
-                                                                            p.Npad, nn, ci, cj);
+                                                                            p.Npad, nn, ci, cj,
+                                                                            reinterpret_cast<double *>(ws + p.table_off));
         FP_CHECK_LAUNCH("cell_setup_kernel");
     }
     CUtensorMap tmap, tmap_w;
@@ -790,7 +797,8 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         const long tiles = n_tiles - t0 < p.slab_tiles ? n_tiles - t0 : p.slab_tiles;
         const long i_first = t0 * TN, slab_rows = tiles * TN;
         dim3 ggrid((unsigned)((p.Npad / WG_COLS + WG_THREADS - 1) / WG_THREADS), (unsigned)(slab_rows / WG_ROWS));
-        weight_planes_kernel<<<ggrid, WG_THREADS, 0, st>>>(ci, cj, i_first, slab_rows, plane_rows, p.Npad, wplanes);
+        weight_planes_kernel<<<ggrid, WG_THREADS, 0, st>>>(ci, cj, reinterpret_cast<const double *>(ws + p.table_off),
+                                                           i_first, slab_rows, plane_rows, p.Npad, wplanes);
         FP_CHECK_LAUNCH("weight_planes_kernel");
         // x: pair of signature blocks * 2 + CTA rank in the pair (fastest: the pairs in flight share
         // a cell tile and with it the weight planes in L2); y: cell tile of the slab
