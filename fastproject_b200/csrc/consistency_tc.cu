@@ -47,6 +47,10 @@
 // regenerated the whole N x N matrix -- 14 times at 3 500 signatures -- and the FP64 generator,
 // not the tensor pipe, bounded the kernel: 14.0 ms per projection against 7.5 ms now.)
 // The FP64 verifier lives in consistency_fp64.cu.
+//
+// Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
+// slabs at small N); FP_TC_DBG (timing experiments only, results are wrong with it set: bit 1
+// MMAs not issued, bit 2 / 4 weight / value planes not loaded).
 #include <stdlib.h>
 
 #include "fp_common.cuh"
