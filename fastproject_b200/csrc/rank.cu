@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256)
 assign_ranks_kernel(const double *__restrict__ scores, const uint32_t *__restrict__ sorted_keys,
                     const int32_t *__restrict__ sorted_cell, const int32_t *__restrict__ row_nan, long rows, long N,
                     long ld, double *__restrict__ out_ranks, long ld_out, int method, LongBin *__restrict__ work,
-                    unsigned *__restrict__ work_count, long row0) {
+                    unsigned *__restrict__ work_count) {
   for (long row = blockIdx.y; row < rows; row += gridDim.y) {
     const uint32_t *ks = sorted_keys + row * ld;
     const int32_t *cs = sorted_cell + row * ld;
@@ -184,7 +184,7 @@ assign_ranks_kernel(const double *__restrict__ scores, const uint32_t *__restric
         if (b - a > kShortBin) {
             if (p == a) {
                 const unsigned slot = atomicAdd(work_count, 1u);
-                work[slot] = LongBin{(int)(row0 + row), (int)a, (int)b, 0};
+                work[slot] = LongBin{(int)row, (int)a, (int)b, 0};      // row: batch-relative
             }
             continue;
         }
@@ -394,7 +394,7 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
         if (gx > 64) gx = 64;
         const unsigned gy = (unsigned)(nb < 32768 ? nb : 32768);
         assign_ranks_kernel<<<dim3(gx, gy), 256, 0, st>>>(src, keys_sorted, cell_sorted, row_nan, nb, N, ld, dst, ld,
-                                                          method, work, work_count, 0);
+                                                          method, work, work_count);
         FP_CHECK_LAUNCH("assign_ranks_kernel");
         long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
                                                                   work_count, big, big_count);
