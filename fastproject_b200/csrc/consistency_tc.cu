@@ -51,6 +51,7 @@
 // Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
 // slabs at small N); FP_TC_DBG (timing experiments only, results are wrong with it set: bit 1
 // MMAs not issued, bit 2 / 4 weight / value planes not loaded).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "fp_common.cuh"
@@ -394,17 +395,20 @@ struct MmaSmem {
     static constexpr int total = bar_off + 256;
 };
 
-// Pair of CTAs: 2 x 127 signatures (+ ones rows) x 128 cells i (tile blockIdx.y of the slab);
-// value planes (A) and weight planes (B) both arrive by TMA.  blockIdx.x = signature-block pair
-// * 2 + CTA rank: pairs that run together share the cell tile, so its weight planes are read
-// from HBM once and from L2 by the other signature blocks.
+// Persistent pairs of CTAs.  A work item is 2 x 127 signatures (+ ones rows) x 128 cells i (one
+// cell tile of the slab); value planes (A) and weight planes (B) both arrive by TMA.  Pair p
+// takes the items p, p + pairs, p + 2 pairs, ... with the pair of signature blocks as the
+// fast index: the pairs in flight share a cell tile, so its weight planes are read from HBM
+// once and from L2 by the other signature blocks.  The barriers, tensor memory and descriptors
+// are set up once per CTA, and the TMA producer runs on into the next item while the epilogue
+// warps drain the accumulators of the current one.
 template <int SR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __grid_constant__ CUtensorMap tmap_weights,
                        const double *__restrict__ values, long ld, double *__restrict__ out, long ld_out, long N,
-                       long K, long Kpad, long i_first, long plane_rows, int n_stages, int chunk_stages,
-                       int output_kind, const unsigned long long *__restrict__ range, const int *__restrict__ flag,
-                       int dbg) {
+                       long K, long Kpad, long i_first, long plane_rows, int n_sig_pairs, int n_items,
+                       int n_stages, int chunk_stages, int output_kind,
+                       const unsigned long long *__restrict__ range, const int *__restrict__ flag, int dbg) {
     using L = MmaSmem<SR>;
     constexpr int STAGES = L::stages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -419,9 +423,8 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    const long tile_row = (long)blockIdx.y * TN;              // slab-relative first cell of the tile
-    const long i0 = i_first + tile_row;
-    const long blk = (long)(blockIdx.x >> 1) * 2 + rank;      // this CTA's block of 127 signatures
+    const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+    const int n_chunks = (n_stages + chunk_stages - 1) / chunk_stages;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -445,28 +448,32 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         // ------------------------------------------------ TMA producer: this CTA's 128 value rows and
         // its 64 of the tile's 128 weight rows, all signalled on the leader's barrier
         if (lane == 0) {
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                // (FP_TC_DBG bits 2 / 4: timing experiments that leave out the weight / value loads)
-                const bool load_a = !(dbg & 4), load_b = !(dbg & 2);
-                if (rank == 0)
-                    mbar_arrive_expect_tx(&full[s], 2 * ((load_a ? SR * A_PLANE_BYTES : 0) +
-                                                         (load_b ? WD * B_PLANE_BYTES : 0)));
-                const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
-                uint8_t *dst = smem + s * L::stage_bytes;
-                if (load_a) {
+            // (FP_TC_DBG bits 2 / 4: timing experiments that leave out the weight / value loads)
+            const bool load_a = !(dbg & 4), load_b = !(dbg & 2);
+            const uint32_t tx_bytes = 2 * ((load_a ? SR * A_PLANE_BYTES : 0) + (load_b ? WD * B_PLANE_BYTES : 0));
+            long g = 0;                                       // stages issued by this CTA so far
+            for (int item = pair; item < n_items; item += n_pairs) {
+                const long tile_row = (long)(item / n_sig_pairs) * TN;       // slab-relative first cell
+                const long blk = (long)(item % n_sig_pairs) * 2 + rank;       // this CTA's block of 127 signatures
+                for (int it = 0; it < n_stages; ++it, ++g) {
+                    const int s = (int)(g % STAGES);
+                    const uint32_t ph = (uint32_t)(g / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], tx_bytes);
+                    const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
+                    uint8_t *dst = smem + s * L::stage_bytes;
+                    if (load_a) {
 #pragma unroll
-                    for (int b = 0; b < SR; ++b)
-                        tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS,
-                                         (int)(b * Kpad + blk * TM), leader_full);
-                }
-                if (load_b) {
+                        for (int b = 0; b < SR; ++b)
+                            tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS,
+                                             (int)(b * Kpad + blk * TM), leader_full);
+                    }
+                    if (load_b) {
 #pragma unroll
-                    for (int a = 0; a < WD; ++a)
-                        tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
-                                         (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+                        for (int a = 0; a < WD; ++a)
+                            tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
+                                             (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+                    }
                 }
             }
         }
@@ -477,34 +484,39 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             const uint32_t idesc = idesc_i8(2 * TM, TN, /*a signed*/ 1, /*b unsigned*/ 0);
             const uint64_t a_desc_base = smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
             const uint64_t b_desc_base = smem_desc(smem_u32(smem) + SR * A_PLANE_BYTES, 16, 1024, LAYOUT_SW128);
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int chunk = it / chunk_stages;
-                const bool chunk_first = it % chunk_stages == 0;
-                if (chunk_first && chunk > 0) {
-                    mbar_wait_cluster(tmem_empty, (chunk - 1) & 1);     // epilogues of both CTAs drained TMEM
-                    tc_fence_after_sync();
-                }
-                mbar_wait_cluster(&full[s], ph);              // both CTAs' operands of this stage
-                tc_fence_after_sync();
-                if (elect_one()) {
-                    const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
-                    const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
-                    if (!(dbg & 1)) {
-                        // K step ks: 32 bytes further along the swizzled rows of both operands
-                        if (chunk_first)
-                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
-                        else
-                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
-#pragma unroll
-                        for (int ks = 1; ks < KS / 32; ++ks)
-                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2), idesc);
+            long g = 0, c = 0;                                // stages / accumulator chunks so far
+            for (int item = pair; item < n_items; item += n_pairs) {
+                for (int it = 0; it < n_stages; ++it, ++g) {
+                    const int s = (int)(g % STAGES);
+                    const uint32_t ph = (uint32_t)(g / STAGES) & 1;
+                    const bool chunk_first = it % chunk_stages == 0;
+                    const bool chunk_last = it % chunk_stages == chunk_stages - 1 || it == n_stages - 1;
+                    if (chunk_first && c > 0) {
+                        mbar_wait_cluster(tmem_empty, (uint32_t)(c - 1) & 1);   // epilogues of both CTAs drained TMEM
+                        tc_fence_after_sync();
                     }
-                    umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
-                    if (it % chunk_stages == chunk_stages - 1 || it == n_stages - 1) umma_commit_pair(accum_full);
+                    mbar_wait_cluster(&full[s], ph);          // both CTAs' operands of this stage
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                        const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
+                        if (!(dbg & 1)) {
+                            // K step ks: 32 bytes further along the swizzled rows of both operands
+                            if (chunk_first)
+                                issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
+                            else
+                                issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
+#pragma unroll
+                            for (int ks = 1; ks < KS / 32; ++ks)
+                                issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2),
+                                                        idesc);
+                        }
+                        umma_commit_pair(&empty[s]);          // frees the stage in both CTAs
+                        if (chunk_last) umma_commit_pair(accum_full);
+                    }
+                    __syncwarp();
+                    if (chunk_last) ++c;
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -513,13 +525,21 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const int row = quad * 32 + lane;
-        const long sig = blk * SIGS_PER_TILE + row;
-        const bool row_live = row < SIGS_PER_TILE && sig < K;
-        const int n_chunks = (n_stages + chunk_stages - 1) / chunk_stages;
+        const Digits dg = decode_range<SR>(range);
+        // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
+        const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
+        const bool invalid = *flag != 0;
+        long c = 0;                                            // accumulator chunks drained so far
 #pragma unroll 1
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        for (int item = pair; item < n_items; item += n_pairs) {
+          const long i0 = i_first + (long)(item / n_sig_pairs) * TN;
+          const long blk = (long)(item % n_sig_pairs) * 2 + rank;
+          const long sig = blk * SIGS_PER_TILE + row;
+          const bool row_live = row < SIGS_PER_TILE && sig < K;
+#pragma unroll 1
+          for (int chunk = 0; chunk < n_chunks; ++chunk, ++c) {
             const bool last = chunk == n_chunks - 1;
-            mbar_wait(accum_full, chunk & 1);
+            mbar_wait(accum_full, (uint32_t)c & 1);
             tc_fence_after_sync();
             // phase A: the ones row (tile row 127) accumulates sum_j W_ij of every column
             if (quad == 3) {
@@ -528,30 +548,28 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     const int col0 = part * 32 + b * 16;
                     uint32_t acc[NCLASS][16];
 #pragma unroll
-                    for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                    for (int cl = 0; cl < NCLASS; ++cl) tmem_ld16(lane_addr + cl * TN + col0, acc[cl]);
                     tmem_ld_wait();
                     if (lane == 31) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             long long d = 0;
 #pragma unroll
-                            for (int c = 0; c < NCLASS; ++c) d += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                            for (int cl = 0; cl < NCLASS; ++cl)
+                                d += (long long)(int)acc[cl][e] << (8 * (NCLASS - 1 - cl));
                             den_s[col0 + e] += (double)d;
                         }
                     }
                 }
             }
             named_barrier_sync(1, EPI_THREADS);
-            const Digits dg = decode_range<SR>(range);
-            // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
-            const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
-            const bool invalid = *flag != 0;
             if (last) {
                 // one division per column instead of one per output; zero row sum -> prediction 0
                 // (Signatures.py:400-402)
                 if (tid - 64 < TN) {
                     const double den = den_s[tid - 64];
                     rden_s[tid - 64] = den > 0.0 ? inv_scale / den : __longlong_as_double(0x7ff8000000000000LL);
+                    den_s[tid - 64] = 0.0;                     // ready for the next item
                 }
                 named_barrier_sync(1, EPI_THREADS);
             }
@@ -560,7 +578,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                 const int col0 = part * 32 + b * 16;
                 uint32_t acc[NCLASS][16];
 #pragma unroll
-                for (int c = 0; c < NCLASS; ++c) tmem_ld16(lane_addr + c * TN + col0, acc[c]);
+                for (int cl = 0; cl < NCLASS; ++cl) tmem_ld16(lane_addr + cl * TN + col0, acc[cl]);
                 tmem_ld_wait();
                 if (row_live) {
                     const long ibase = i0 + col0;
@@ -571,7 +589,8 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                         if (ibase + e >= N) continue;
                         long long num = 0;
 #pragma unroll
-                        for (int c = 0; c < NCLASS; ++c) num += (long long)(int)acc[c][e] << (8 * (NCLASS - 1 - c));
+                        for (int cl = 0; cl < NCLASS; ++cl)
+                            num += (long long)(int)acc[cl][e] << (8 * (NCLASS - 1 - cl));
                         // partial sums of earlier j chunks are parked in the output row
                         double total = (double)num;
                         if (chunk > 0) total += orow[e];
@@ -588,12 +607,13 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     }
                 }
             }
-            if (!last) {
-                // TMEM may be overwritten by the next chunk once every epilogue warp of the pair is done
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
-            }
+            // TMEM may be overwritten by the next chunk (of this or the next item) once every
+            // epilogue warp of the pair has read it
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
+            // (rden_s is rewritten at the end of the next item at the earliest, two named barriers on)
+          }
         }
     }
     tc_fence_before_sync();
@@ -688,6 +708,35 @@ bool make_plan(long N, long K, Plan *p) {
     return true;
 }
 
+}  // namespace
+
+namespace {
+// CTA pairs of the persistent kernel that can be resident at once (a GPC with an odd number of
+// free SMs leaves one unpaired): the grid must not exceed it, or a late pair would start its
+// share of the items when the others are done.
+template <int SR>
+int resident_pairs() {
+    static int cached = 0;
+    if (cached) return cached;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)fp::sm_count());
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = MmaSmem<SR>::total;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, consistency_mma_kernel<SR>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = fp::sm_count() / 2;
+    }
+    cached = n;
+    return n;
+}
 }  // namespace
 
 size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K) {
@@ -804,17 +853,21 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         weight_planes_kernel<<<ggrid, WG_THREADS, 0, st>>>(ci, cj, reinterpret_cast<const double *>(ws + p.table_off),
                                                            i_first, slab_rows, plane_rows, p.Npad, wplanes);
         FP_CHECK_LAUNCH("weight_planes_kernel");
-        // x: pair of signature blocks * 2 + CTA rank in the pair (fastest: the pairs in flight share
-        // a cell tile and with it the weight planes in L2); y: cell tile of the slab
-        dim3 grid((unsigned)p.nblk, (unsigned)tiles);
+        // persistent CTA pairs: one per pair of SMs, or fewer when the slab has fewer items
+        const int n_sig_pairs = (int)(p.nblk / 2);
+        const long n_items = tiles * n_sig_pairs;
+        long n_pairs = p.sr == 2 ? resident_pairs<2>() : resident_pairs<3>();
+        if (dbg & 8) fprintf(stderr, "consistency_mma_kernel: %ld resident CTA pairs, %ld items\n", n_pairs, n_items);
+        if (n_pairs > n_items) n_pairs = n_items;
+        dim3 grid((unsigned)(2 * n_pairs));
         if (p.sr == 2)
             consistency_mma_kernel<2><<<grid, THREADS, MmaSmem<2>::total, st>>>(
-                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_stages, n_stages,
-                output_kind, range, flag, dbg);
+                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
+                n_stages, n_stages, output_kind, range, flag, dbg);
         else
             consistency_mma_kernel<3><<<grid, THREADS, MmaSmem<3>::total, st>>>(
-                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_stages, CHUNK_STAGES_3,
-                output_kind, range, flag, dbg);
+                tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
+                n_stages, CHUNK_STAGES_3, output_kind, range, flag, dbg);
         FP_CHECK_LAUNCH("consistency_mma_kernel");
     }
     return FP_OK;
