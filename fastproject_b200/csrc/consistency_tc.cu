@@ -49,9 +49,8 @@
 // The FP64 verifier lives in consistency_fp64.cu.
 //
 // Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
-// slabs at small N); FP_TC_DBG (timing experiments only, results are wrong with it set: bit 1
-// MMAs not issued, bit 2 / 4 weight / value planes not loaded).
-#include <stdio.h>
+// slabs at small N); FP_TC_DBG=1 (timing experiments only, results are wrong with it set: the
+// MMAs are not issued).
 #include <stdlib.h>
 
 #include "fp_common.cuh"
@@ -391,9 +390,11 @@ struct MmaSmem {
     static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
     static constexpr int den_off = stages * stage_bytes;     // sum_j W_ij per column, then its scaled reciprocal
     static constexpr int rden_off = den_off + TN * 8;
-    static constexpr int bar_off = rden_off + TN * 8;
+    static constexpr int epi_off = rden_off + TN * 8;        // per epilogue warp: 32 rows x 8 columns of doubles
+    static constexpr int bar_off = epi_off + EPI_WARPS * 2048;
     static constexpr int total = bar_off + 256;
 };
+static_assert(MmaSmem<2>::total <= 232448 && MmaSmem<3>::total <= 232448, "shared memory of the MMA kernel");
 
 // Persistent pairs of CTAs.  A work item is 2 x 127 signatures (+ ones rows) x 128 cells i (one
 // cell tile of the slab); value planes (A) and weight planes (B) both arrive by TMA.  Pair p
@@ -415,6 +416,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
     uint8_t *smem = smem_raw;
     double *den_s = reinterpret_cast<double *>(smem + L::den_off);
     double *rden_s = reinterpret_cast<double *>(smem + L::rden_off);
+    double *epi_s = reinterpret_cast<double *>(smem + L::epi_off);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::bar_off);          // [STAGES] leader's are used
     uint64_t *empty = full + 4;                                                  // [STAGES] one per CTA
     uint64_t *accum_full = empty + 4;                                            // one per CTA
@@ -448,9 +450,9 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         // ------------------------------------------------ TMA producer: this CTA's 128 value rows and
         // its 64 of the tile's 128 weight rows, all signalled on the leader's barrier
         if (lane == 0) {
-            // (FP_TC_DBG bits 2 / 4: timing experiments that leave out the weight / value loads)
-            const bool load_a = !(dbg & 4), load_b = !(dbg & 2);
-            const uint32_t tx_bytes = 2 * ((load_a ? SR * A_PLANE_BYTES : 0) + (load_b ? WD * B_PLANE_BYTES : 0));
+            // both CTAs' bytes of a stage are counted on the leader's barrier: the leader cannot run
+            // ahead of a peer that has not issued its loads, so neither producer is ever lapped
+            constexpr uint32_t tx_bytes = 2 * L::stage_bytes;
             long g = 0;                                       // stages issued by this CTA so far
             for (int item = pair; item < n_items; item += n_pairs) {
                 const long tile_row = (long)(item / n_sig_pairs) * TN;       // slab-relative first cell
@@ -462,18 +464,14 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     if (rank == 0) mbar_arrive_expect_tx(&full[s], tx_bytes);
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
                     uint8_t *dst = smem + s * L::stage_bytes;
-                    if (load_a) {
 #pragma unroll
-                        for (int b = 0; b < SR; ++b)
-                            tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS,
-                                             (int)(b * Kpad + blk * TM), leader_full);
-                    }
-                    if (load_b) {
+                    for (int b = 0; b < SR; ++b)
+                        tma_load_2d_pair(dst + b * A_PLANE_BYTES, &tmap_values, it * KS, (int)(b * Kpad + blk * TM),
+                                         leader_full);
 #pragma unroll
-                        for (int a = 0; a < WD; ++a)
-                            tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
-                                             (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
-                    }
+                    for (int a = 0; a < WD; ++a)
+                        tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
+                                         (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
                 }
             }
         }
@@ -524,7 +522,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31
         const int part = (warp - 2) >> 2;                      // columns 32*part .. +31 (4 warps per quadrant)
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        const int row = quad * 32 + lane;
+        double *stage = epi_s + (warp - 2) * 256;
         const Digits dg = decode_range<SR>(range);
         // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
         const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
@@ -534,8 +532,6 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         for (int item = pair; item < n_items; item += n_pairs) {
           const long i0 = i_first + (long)(item / n_sig_pairs) * TN;
           const long blk = (long)(item % n_sig_pairs) * 2 + rank;
-          const long sig = blk * SIGS_PER_TILE + row;
-          const bool row_live = row < SIGS_PER_TILE && sig < K;
 #pragma unroll 1
           for (int chunk = 0; chunk < n_chunks; ++chunk, ++c) {
             const bool last = chunk == n_chunks - 1;
@@ -573,6 +569,12 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                 }
                 named_barrier_sync(1, EPI_THREADS);
             }
+            // Output.  A thread holds one signature row x 16 columns (TMEM lane = row), so writing
+            // from that layout sends every store to 32 different rows (32 L1 wavefronts per
+            // instruction; measured ~38 us per item, a sixth of the kernel).  The exact sums go
+            // through a per-warp 32 x 8 staging tile (XOR-swizzled: two-way conflicts only, the
+            // minimum for 8-byte words) and come back with 8 consecutive columns of 4 rows per
+            // instruction: all global reads and writes are 64-byte row segments.
 #pragma unroll 1
             for (int b = 0; b < 2; ++b) {
                 const int col0 = part * 32 + b * 16;
@@ -580,31 +582,42 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
 #pragma unroll
                 for (int cl = 0; cl < NCLASS; ++cl) tmem_ld16(lane_addr + cl * TN + col0, acc[cl]);
                 tmem_ld_wait();
-                if (row_live) {
-                    const long ibase = i0 + col0;
-                    double *orow = out + sig * ld_out + ibase;
-                    const double *vrow = values + sig * ld + ibase;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        if (ibase + e >= N) continue;
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
                         long long num = 0;
 #pragma unroll
                         for (int cl = 0; cl < NCLASS; ++cl)
-                            num += (long long)(int)acc[cl][e] << (8 * (NCLASS - 1 - cl));
-                        // partial sums of earlier j chunks are parked in the output row
-                        double total = (double)num;
-                        if (chunk > 0) total += orow[e];
-                        if (!last) {
-                            orow[e] = total;
-                            continue;
-                        }
-                        // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2
-                        const double rden = rden_s[col0 + e];
-                        double r = rden == rden ? 0.5 * (total * rden + centre) : 0.0;
-                        if (output_kind == FP_OUT_ABS_ERROR) r = fabs(vrow[e] - r);
-                        if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
-                        orow[e] = r;
+                            num += (long long)(int)acc[cl][8 * h + e] << (8 * (NCLASS - 1 - cl));
+                        stage[lane * 8 + (e ^ ((lane >> 1) & 7))] = (double)num;
                     }
+                    __syncwarp();
+                    const int cc = lane & 7;
+                    const long col = i0 + col0 + 8 * h + cc;
+                    const double rden = rden_s[col0 + 8 * h + cc];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = 4 * k + (lane >> 3);              // row within this warp's TMEM quadrant
+                        double total = stage[rr * 8 + (cc ^ ((rr >> 1) & 7))];
+                        const int trow = quad * 32 + rr;
+                        const long tsig = blk * SIGS_PER_TILE + trow;
+                        if (trow < SIGS_PER_TILE && tsig < K && col < N) {
+                            double *optr = out + tsig * ld_out + col;
+                            // partial sums of earlier j chunks are parked in the output row
+                            if (chunk > 0) total += *optr;
+                            if (!last) {
+                                *optr = total;
+                            } else {
+                                // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2
+                                double r = rden == rden ? 0.5 * (total * rden + centre) : 0.0;
+                                if (output_kind == FP_OUT_ABS_ERROR) r = fabs(values[tsig * ld + col] - r);
+                                if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
+                                *optr = r;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             // TMEM may be overwritten by the next chunk (of this or the next item) once every
@@ -857,7 +870,6 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         const int n_sig_pairs = (int)(p.nblk / 2);
         const long n_items = tiles * n_sig_pairs;
         long n_pairs = p.sr == 2 ? resident_pairs<2>() : resident_pairs<3>();
-        if (dbg & 8) fprintf(stderr, "consistency_mma_kernel: %ld resident CTA pairs, %ld items\n", n_pairs, n_items);
         if (n_pairs > n_items) n_pairs = n_items;
         dim3 grid((unsigned)(2 * n_pairs));
         if (p.sr == 2)
