@@ -582,6 +582,14 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
 #pragma unroll
                 for (int cl = 0; cl < NCLASS; ++cl) tmem_ld16(lane_addr + cl * TN + col0, acc[cl]);
                 tmem_ld_wait();
+                if (b == 1) {
+                    // this warp's last read of tensor memory: the next chunk (of this or the next item)
+                    // may overwrite it once every epilogue warp of the pair has got this far -- the
+                    // arithmetic and the global traffic below no longer hold the MMAs back
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -620,11 +628,6 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     __syncwarp();
                 }
             }
-            // TMEM may be overwritten by the next chunk (of this or the next item) once every
-            // epilogue warp of the pair has read it
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(tmem_empty), 0));
             // (rden_s is rewritten at the end of the next item at the earliest, two named barriers on)
           }
         }
