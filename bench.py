@@ -292,9 +292,9 @@ def run_b200(args):
     cons_flops = 2.0 * N * N * (n_rows + 1)                   # per launch (one projection)
     score_bytes = G * N * 16.0 + N * n_rows * 8.0 + 5.0 * nnz  # per launch
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of
-    # this exact configuration (profiles/r01_summary_tc.md); None where no capture exists
-    # (tc: weight_planes_kernel 0.0013 + 1.5579 GB and consistency_mma_kernel 7.5027 + 0.6680 GB)
-    ncu_traffic = {("C2", "tc", 1): 1338000 + 1557907000 + 7502659000 + 667994000,
+    # this exact configuration (profiles/r01_summary_slab.md); None where no capture exists
+    # (tc: weight_planes_kernel 0.0043 + 1.5572 GB and consistency_mma_kernel 12.4369 + 0.6883 GB)
+    ncu_traffic = {("C2", "tc", 1): 4314000 + 1557239000 + 12436882000 + 688290000,
                    ("C2", "fp64", 1): 603465984 + 551192064}
     roofline = dict(bound="tensor", kernel="fp_consistency[%s]" % precision,
                     achieved=cons_flops / (cons_ms * 1e-3) / 1e12, peak=peaks["tflops"],
