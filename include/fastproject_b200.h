@@ -180,10 +180,12 @@ int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t ld, double 
  * fp_consistency -- for one projection, the local dissimilarity
  *   D[k,i] = | r[k,i] - sum_j w_ij r[k,j] / sum_j w_ij |,
  *   w_ij = exp(-|p_i - p_j|^2 / sigma_sq_i), w_ii = 0, (sum_j w_ij == 0 -> 1)
- * without materialising the N x N kernel matrix.  Replaces Signatures.py:396-408
- * and :412-413 (cdist, exp, zeroed diagonal, row normalisation, both np.dot
- * calls and the |actual - predicted| step) for real and random signatures in
- * one call.
+ * Replaces Signatures.py:396-408 and :412-413 (cdist, exp, zeroed diagonal, row
+ * normalisation, both np.dot calls and the |actual - predicted| step) for real and
+ * random signatures in one call.  The N x N kernel matrix never exists as doubles:
+ * FP_PRECISION_FP64 recomputes it tile by tile; FP_PRECISION_TC keeps it as four 8-bit
+ * digit planes (4 bytes per weight) in the caller's workspace, generated once per call
+ * in slabs of cells (at most FASTPROJECT_B200_SLAB_BYTES, default 6 GiB, at a time).
  *   coords       : 2 x N float64 (x row then y row)
  *   sigma_sq     : per-cell bandwidth^2 (N float64) or NULL to use sigma_sq_scalar
  *                  (the reference has a single NEIGHBORHOOD_SIZE**2, :398)
@@ -191,6 +193,9 @@ int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t ld, double 
  *   out_dissim   : K x ld_out float64
  *   output_kind  : FP_OUT_*  (the factor branch, :493-508, needs the raw prediction)
  *   precision_mode : FP_PRECISION_*
+ *   workspace    : fp_consistency_workspace_bytes(N, K, mode) bytes, 1024-byte aligned
+ *                  (0 for FP_PRECISION_FP64); FP_REUSE_PACKED needs the same workspace
+ *                  as the previous call
  */
 size_t fp_consistency_workspace_bytes(int64_t N, int64_t K, int precision_mode);
 int fp_consistency(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
