@@ -85,4 +85,30 @@ __device__ double np_pairwise_sum(Load load, long lo, long n) {
     }
 }
 
+// One leaf of that tree (8 <= n <= 128) summed by EIGHT consecutive lanes: lane k owns the
+// accumulator r_k of the reference loop (elements k, k + 8, ... in order), the eight partial
+// sums are combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) by an xor-shuffle tree (IEEE
+// addition is commutative, so both partners of a shuffle compute the same bits), and the
+// n % 8 tail is added sequentially.  Same operations in the same order as np_pairwise_sum on
+// the leaf, with 64-byte coalesced loads and eight times the threads at work.  All 32 lanes of
+// the warp must call it (lanes whose leaf is a dummy pass any valid leaf).
+template <typename Load>
+__device__ __forceinline__ double np_leaf_sum_octet(Load load, long lo, long n) {
+    const int k = threadIdx.x & 7;
+    const long body = n - (n % 8);
+    double r = load(lo + k);
+    long i = 8;
+    for (; i + 24 < body; i += 32) {                 // four loads in flight, added in order
+        const double a = load(lo + i + k), b = load(lo + i + 8 + k), c = load(lo + i + 16 + k),
+                     d = load(lo + i + 24 + k);
+        r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r, a), b), c), d);
+    }
+    for (; i < body; i += 8) r = __dadd_rn(r, load(lo + i + k));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    for (i = body; i < n; ++i) r = __dadd_rn(r, load(lo + i));
+    return r;
+}
+
 }  // namespace fp

@@ -51,14 +51,12 @@ row_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double 
     __shared__ double stat[2];
     for (long g = blockIdx.x; g < G; g += gridDim.x) {
         const double *row = X + g * ld;
-        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
-            leaf_sum[l] = fp::np_pairwise_sum(RowLoad{row}, leaves[l].lo, leaves[l].n);
+        fp::rowtree::leaf_sums(RowLoad{row}, leaves, n_leaves, leaf_sum);
         __syncthreads();
         if (threadIdx.x == 0) stat[0] = __ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N);
         __syncthreads();
         const double mean = stat[0];
-        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
-            leaf_sum[l] = fp::np_pairwise_sum(RowSqDev{row, mean}, leaves[l].lo, leaves[l].n);
+        fp::rowtree::leaf_sums(RowSqDev{row, mean}, leaves, n_leaves, leaf_sum);
         __syncthreads();
         if (threadIdx.x == 0) {
             double sd = sqrt(__ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N));
@@ -73,22 +71,53 @@ row_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double 
     }
 }
 
-// axis = 0: plain sequential sums over the rows, one thread per column (coalesced)
-__global__ void __launch_bounds__(128)
+// axis = 0: plain sequential sums over the rows, one thread per column (coalesced).  Only
+// N threads exist, so every thread keeps COL_DEPTH loads in flight; the additions stay in
+// row order.
+constexpr int COL_DEPTH = 16;
+
+__global__ void __launch_bounds__(64)
 col_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
+    const double *col = X + c;
     double s = 0.0;
-    for (long g = 0; g < G; ++g) s = __dadd_rn(s, X[g * ld + c]);
+    long g = 0;
+    for (; g + COL_DEPTH <= G; g += COL_DEPTH) {
+        double v[COL_DEPTH];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) v[q] = col[(g + q) * ld];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) s = __dadd_rn(s, v[q]);
+    }
+    for (; g < G; ++g) s = __dadd_rn(s, col[g * ld]);
     const double mean = __ddiv_rn(s, (double)G);
     double s2 = 0.0;
-    for (long g = 0; g < G; ++g) {
-        const double d = __dsub_rn(X[g * ld + c], mean);
+    for (g = 0; g + COL_DEPTH <= G; g += COL_DEPTH) {
+        double v[COL_DEPTH];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) v[q] = col[(g + q) * ld];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) {
+            const double d = __dsub_rn(v[q], mean);
+            s2 = __dadd_rn(s2, __dmul_rn(d, d));
+        }
+    }
+    for (; g < G; ++g) {
+        const double d = __dsub_rn(col[g * ld], mean);
         s2 = __dadd_rn(s2, __dmul_rn(d, d));
     }
     double sd = sqrt(__ddiv_rn(s2, (double)G));
     if (sd == 0.0) sd = 1.0;
-    for (long g = 0; g < G; ++g) out[g * ld_out + c] = __ddiv_rn(__dsub_rn(X[g * ld + c], mean), sd);
+    double *ocol = out + c;
+    for (g = 0; g + COL_DEPTH <= G; g += COL_DEPTH) {
+        double v[COL_DEPTH];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) v[q] = col[(g + q) * ld];
+#pragma unroll
+        for (int q = 0; q < COL_DEPTH; ++q) ocol[(g + q) * ld_out] = __ddiv_rn(__dsub_rn(v[q], mean), sd);
+    }
+    for (; g < G; ++g) ocol[g * ld_out] = __ddiv_rn(__dsub_rn(col[g * ld], mean), sd);
 }
 
 }  // namespace
@@ -147,7 +176,7 @@ extern "C" int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t 
     FP_CHECK_ARG(X && out, "fp_normalize_cols: null pointer");
     FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N, "fp_normalize_cols: bad shape G=%ld N=%ld", (long)G,
                  (long)N);
-    col_zscore_kernel<<<(unsigned)((N + 127) / 128), 128, 0, fp::as_stream(stream)>>>(X, G, N, ld, out, ld_out);
+    col_zscore_kernel<<<(unsigned)((N + 63) / 64), 64, 0, fp::as_stream(stream)>>>(X, G, N, ld, out, ld_out);
     FP_CHECK_LAUNCH("col_zscore_kernel");
     return FP_OK;
 }

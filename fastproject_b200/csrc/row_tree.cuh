@@ -35,6 +35,24 @@ __device__ inline double fold_tree(const double *leaf_sum, const int *__restrict
     return stack[0];
 }
 
+// leaf sums of one row for the whole CTA: eight lanes per leaf (blockDim.x a multiple of 32);
+// a row shorter than 8 elements is a single short leaf summed by one thread
+template <typename Load>
+__device__ __forceinline__ void leaf_sums(Load load, const Leaf *__restrict__ leaves, int n_leaves, double *leaf_sum) {
+    if (n_leaves == 1 && leaves[0].n < 8) {
+        if (threadIdx.x == 0) leaf_sum[0] = fp::np_pairwise_sum(load, leaves[0].lo, leaves[0].n);
+        return;
+    }
+    const int per_pass = blockDim.x >> 3;
+    for (int base = 0; base < n_leaves; base += per_pass) {
+        const int l = base + (threadIdx.x >> 3);
+        const bool live = l < n_leaves;
+        const Leaf leaf = leaves[live ? l : 0];
+        const double v = fp::np_leaf_sum_octet(load, leaf.lo, leaf.n);
+        if (live && (threadIdx.x & 7) == 0) leaf_sum[l] = v;
+    }
+}
+
 inline void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
     if (depth > max_depth) max_depth = depth;
     if (n <= 128) {

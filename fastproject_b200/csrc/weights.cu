@@ -70,11 +70,9 @@ compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ 
     for (long g = blockIdx.x; g < G; g += gridDim.x) {
         const double *row = X + g * ld;
         const double *prow = P_nd ? P_nd + g * ld_pnd : nullptr;
-        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x) {
-            sum_a[l] = fp::np_pairwise_sum(DetectedValue{row, prow}, leaves[l].lo, leaves[l].n);
-            sum_b[l] = fp::np_pairwise_sum(Detected{row, prow}, leaves[l].lo, leaves[l].n);
-            sum_c[l] = fp::np_pairwise_sum(NotDetected{row, prow}, leaves[l].lo, leaves[l].n);
-        }
+        fp::rowtree::leaf_sums(DetectedValue{row, prow}, leaves, n_leaves, sum_a);
+        fp::rowtree::leaf_sums(Detected{row, prow}, leaves, n_leaves, sum_b);
+        fp::rowtree::leaf_sums(NotDetected{row, prow}, leaves, n_leaves, sum_c);
         __syncthreads();
         if (threadIdx.x == 0) {
             const double sxp = fold_tree(sum_a, prog, n_prog, stack);
@@ -85,8 +83,7 @@ compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ 
         }
         __syncthreads();
         const double mu = stat[0];
-        for (int l = threadIdx.x; l < n_leaves; l += blockDim.x)
-            sum_a[l] = fp::np_pairwise_sum(ExpressedDetect{mu, params, ldp}, leaves[l].lo, leaves[l].n);
+        fp::rowtree::leaf_sums(ExpressedDetect{mu, params, ldp}, leaves, n_leaves, sum_a);
         __syncthreads();
         if (threadIdx.x == 0) {
             const double mean_pde = __ddiv_rn(fold_tree(sum_a, prog, n_prog, stack), (double)N);
