@@ -28,19 +28,109 @@ struct GroupSquaredDev {
     }
 };
 
-__global__ void background_stats_kernel(const double *__restrict__ rnd_med,
-                                        const int32_t *__restrict__ rnd_order,
-                                        const int32_t *__restrict__ group_ptr, long n_groups,
-                                        double *__restrict__ out_mu, double *__restrict__ out_sigma) {
-    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
+// Block form: one CTA per group.  Thread 0 enumerates the leaves of NumPy's pairwise tree for
+// this group's size and its post-order program (the recursion of fp::np_pairwise_sum, made
+// iterative), eight lanes sum each leaf, thread 0 folds.  A group of 500 medians took 116 us
+// with one thread walking both sums.
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_MAX_LEAVES = 1024;
+
+struct StatLeaf {
+    int lo, n;
+};
+
+__device__ void stats_build_tree(long lo, long n, StatLeaf *leaves, int *n_leaves, int *prog, int *n_prog) {
+    long st_lo[48], st_n[48];
+    int st_seen[48];
+    int sp = 0, nl = 0, np = 0;
+    st_lo[0] = lo; st_n[0] = n; st_seen[0] = 0; sp = 1;
+    while (sp) {
+        const long flo = st_lo[sp - 1], fn = st_n[sp - 1];
+        if (fn <= 128) {
+            prog[np++] = nl;
+            leaves[nl].lo = (int)flo;
+            leaves[nl].n = (int)fn;
+            ++nl;
+            --sp;
+        } else if (!st_seen[sp - 1]) {
+            st_seen[sp - 1] = 1;
+            long n2 = fn / 2;
+            n2 -= n2 % 8;
+            st_lo[sp] = flo + n2; st_n[sp] = fn - n2; st_seen[sp] = 0; ++sp;     // right half: visited second
+            st_lo[sp] = flo; st_n[sp] = n2; st_seen[sp] = 0; ++sp;               // left half: visited first
+        } else {
+            prog[np++] = -1;                     // both halves summed: add them
+            --sp;
+        }
+    }
+    *n_leaves = nl;
+    *n_prog = np;
+}
+
+template <typename Load>
+__device__ double stats_tree_sum(Load load, const StatLeaf *leaves, int n_leaves, const int *prog, int n_prog,
+                                 double *leaf_sum, double *bcast) {
+    if (n_leaves == 1 && leaves[0].n < 8) {
+        if (threadIdx.x == 0) leaf_sum[0] = fp::np_pairwise_sum(load, leaves[0].lo, leaves[0].n);
+    } else {
+        const int per_pass = STATS_THREADS >> 3;
+        for (int base = 0; base < n_leaves; base += per_pass) {
+            const int l = base + (threadIdx.x >> 3);
+            const bool live = l < n_leaves;
+            const StatLeaf leaf = leaves[live ? l : 0];
+            const double v = fp::np_leaf_sum_octet(load, leaf.lo, leaf.n);
+            if (live && (threadIdx.x & 7) == 0) leaf_sum[l] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double stack[48];
+        int sp = 0;
+        for (int p = 0; p < n_prog; ++p) {
+            const int op = prog[p];
+            if (op >= 0) stack[sp++] = leaf_sum[op];
+            else {
+                const double b = stack[--sp], a = stack[--sp];
+                stack[sp++] = __dadd_rn(a, b);
+            }
+        }
+        *bcast = stack[0];
+    }
+    __syncthreads();
+    return *bcast;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+background_stats_kernel(const double *__restrict__ rnd_med, const int32_t *__restrict__ rnd_order,
+                        const int32_t *__restrict__ group_ptr, long n_groups, double *__restrict__ out_mu,
+                        double *__restrict__ out_sigma) {
+    __shared__ StatLeaf leaves[STATS_MAX_LEAVES];
+    __shared__ int prog[2 * STATS_MAX_LEAVES];
+    __shared__ double leaf_sum[STATS_MAX_LEAVES];
+    __shared__ int n_leaves, n_prog;
+    __shared__ double bcast;
+    const long g = blockIdx.x;
     const long lo = group_ptr[g], n = group_ptr[g + 1] - lo;
     GroupValue val{rnd_med, rnd_order};
-    const double mean = __ddiv_rn(fp::np_pairwise_sum(val, lo, n), (double)n);
+    if (n > 60L * STATS_MAX_LEAVES) {
+        // more leaves than the table holds (a leaf has at least 60 elements): one thread, serially
+        if (threadIdx.x == 0) {
+            const double mean = __ddiv_rn(fp::np_pairwise_sum(val, lo, n), (double)n);
+            GroupSquaredDev dev{rnd_med, rnd_order, mean};
+            out_mu[g] = mean;
+            out_sigma[g] = sqrt(__ddiv_rn(fp::np_pairwise_sum(dev, lo, n), (double)n));
+        }
+        return;
+    }
+    if (threadIdx.x == 0) stats_build_tree(lo, n, leaves, &n_leaves, prog, &n_prog);
+    __syncthreads();
+    const double mean = __ddiv_rn(stats_tree_sum(val, leaves, n_leaves, prog, n_prog, leaf_sum, &bcast), (double)n);
     GroupSquaredDev dev{rnd_med, rnd_order, mean};
-    const double var = __ddiv_rn(fp::np_pairwise_sum(dev, lo, n), (double)n);
-    out_mu[g] = mean;
-    out_sigma[g] = sqrt(var);
+    const double var = __ddiv_rn(stats_tree_sum(dev, leaves, n_leaves, prog, n_prog, leaf_sum, &bcast), (double)n);
+    if (threadIdx.x == 0) {
+        out_mu[g] = mean;
+        out_sigma[g] = sqrt(var);
+    }
 }
 
 __device__ double normal_cdf(double z) {
@@ -77,8 +167,8 @@ extern "C" int fp_background_pvalues(const double *med, const int32_t *sig_group
                  "argmin of an empty sequence, Signatures.py:437)");
     cudaStream_t st = fp::as_stream(stream);
     if (n_groups > 0) {
-        background_stats_kernel<<<(unsigned)((n_groups + 31) / 32), 32, 0, st>>>(
-            rnd_med, rnd_order, group_ptr, n_groups, out_mu, out_sigma);
+        background_stats_kernel<<<(unsigned)n_groups, STATS_THREADS, 0, st>>>(rnd_med, rnd_order, group_ptr, n_groups,
+                                                                             out_mu, out_sigma);
         FP_CHECK_LAUNCH("background_stats_kernel");
     }
     if (K > 0) {
