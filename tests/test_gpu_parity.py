@@ -244,6 +244,28 @@ def test_background_pvalues_vs_oracle(fp):
     np.testing.assert_allclose(p.cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+def test_background_stats_tree_shapes(fp):
+    """Group sizes on every side of the pairwise tree's thresholds (short loop below 8, one leaf up
+    to 128, splits rounded to multiples of 8): mean and std bit-identical to NumPy."""
+    import torch
+    rng = np.random.RandomState(10)
+    sizes = [1, 2, 7, 8, 9, 127, 128, 129, 255, 1000, 4099, 20011]
+    rnd_ng = [int(v) for v in np.repeat(np.arange(1, len(sizes) + 1), sizes)]
+    rng.shuffle(rnd_ng)
+    rmed = rng.normal(loc=500, scale=4, size=len(rnd_ng))
+    real_ng = [int(v) for v in rng.randint(1, len(sizes) + 1, size=40)]
+    med = rng.normal(loc=497, scale=5, size=40)
+    table = O.background_table(rmed, rnd_ng)
+    want = O.background_pvalues(med, real_ng, table)
+    order, ptr, grp = fp.S._background_groups(rnd_ng, real_ng)
+    t = lambda a, dt: torch.from_numpy(np.asarray(a)).to("cuda", dt)
+    p, mu, sd = fp.E.background_pvalues(t(med, torch.float64), t(grp, torch.int32), t(rmed, torch.float64),
+                                        t(order, torch.int32), t(ptr, torch.int32))
+    assert np.array_equal(mu.cpu().numpy(), table[:, 1])
+    assert np.array_equal(sd.cpu().numpy(), table[:, 2])
+    np.testing.assert_allclose(p.cpu().numpy(), want, rtol=1e-12, atol=0, equal_nan=True)
+
+
 # ------------------------------------------------------------------ consistency
 def _svp(fp, c, extra=None, **kw):
     data = _data(fp, c)
