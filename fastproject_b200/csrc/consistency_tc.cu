@@ -51,7 +51,11 @@
 // Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
 // slabs at small N); FP_TC_DBG=1 (timing experiments only, results are wrong with it set: the
 // MMAs are not issued).
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <cub/device/device_scan.cuh>
 
 #include "fp_common.cuh"
 #include "tc_common.cuh"
@@ -89,6 +93,15 @@ struct __align__(32) CellJ { double x, y, nb, pad; };         // column side
 __device__ __forceinline__ unsigned long long dist_key(double v) {   // v >= 0: bit pattern is monotone
     return (unsigned long long)__double_as_longlong(v);
 }
+// order-preserving 64-bit key of any double, and back (ranges and bounding boxes by atomicMin / Max)
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_key(unsigned long long key) {
+    const unsigned long long u = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+    return __longlong_as_double((long long)u);
+}
 
 // nearest-neighbour squared distance of every cell; the j range is split over blockIdx.y and
 // combined with atomicMin (non-negative doubles order like their bit patterns)
@@ -117,6 +130,138 @@ nearest_neighbour_kernel(const double *__restrict__ coords, long N, unsigned lon
         __syncthreads();
     }
     if (live) atomicMin(&nn[i], dist_key(m));
+}
+
+// ---------------------------------------------------------------------------
+// The same minimum through a uniform grid (about one cell of the projection per grid cell):
+// cells are counting-sorted by grid cell, and every cell searches the Chebyshev rings around
+// its own grid cell until the best distance found is no larger than the distance to the border
+// of the block searched so far.  The squared distances are the brute-force kernel's
+// (fma(dx, dx, dy * dy) of the same differences), so the result is bit-identical to it; only
+// the candidates differ.  O(N) for spread-out projections instead of O(N^2) (0.25 ms at
+// 20 000 cells, 6 ms at 100 000, 0.6 s at 1 000 000 for the brute-force kernel).
+// ---------------------------------------------------------------------------
+struct NnGrid {
+    double xmin, ymin, hx, hy, inv_hx, inv_hy;
+};
+
+// bounds[0..1]: ordered keys of min x, min y (initialised to all ones); [2..3]: max x, max y (zero)
+__global__ void __launch_bounds__(256)
+nn_bounds_kernel(const double *__restrict__ coords, long N, unsigned long long *__restrict__ bounds) {
+    unsigned long long lo_x = ~0ull, lo_y = ~0ull, hi_x = 0ull, hi_y = 0ull;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long)gridDim.x * 256) {
+        const unsigned long long kx = ordered_key(coords[i]), ky = ordered_key(coords[N + i]);
+        lo_x = kx < lo_x ? kx : lo_x;
+        hi_x = kx > hi_x ? kx : hi_x;
+        lo_y = ky < lo_y ? ky : lo_y;
+        hi_y = ky > hi_y ? ky : hi_y;
+    }
+    for (int off = 16; off; off >>= 1) {
+        unsigned long long o;
+        o = __shfl_xor_sync(0xffffffffu, lo_x, off); lo_x = o < lo_x ? o : lo_x;
+        o = __shfl_xor_sync(0xffffffffu, lo_y, off); lo_y = o < lo_y ? o : lo_y;
+        o = __shfl_xor_sync(0xffffffffu, hi_x, off); hi_x = o > hi_x ? o : hi_x;
+        o = __shfl_xor_sync(0xffffffffu, hi_y, off); hi_y = o > hi_y ? o : hi_y;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bounds[0], lo_x);
+        atomicMin(&bounds[1], lo_y);
+        atomicMax(&bounds[2], hi_x);
+        atomicMax(&bounds[3], hi_y);
+    }
+}
+
+__device__ __forceinline__ NnGrid nn_grid_of(const unsigned long long *__restrict__ bounds, int G) {
+    NnGrid g;
+    g.xmin = from_ordered_key(bounds[0]);
+    g.ymin = from_ordered_key(bounds[1]);
+    const double wx = from_ordered_key(bounds[2]) - g.xmin, wy = from_ordered_key(bounds[3]) - g.ymin;
+    g.hx = wx > 0.0 ? wx / G : 1.0;
+    g.hy = wy > 0.0 ? wy / G : 1.0;
+    g.inv_hx = 1.0 / g.hx;
+    g.inv_hy = 1.0 / g.hy;
+    return g;
+}
+__device__ __forceinline__ int nn_cell_coord(double v, double vmin, double inv_h, int G) {
+    const double t = (v - vmin) * inv_h;
+    int c = t >= (double)G ? G - 1 : (int)t;      // also catches the maximum (t == G)
+    if (c < 0) c = 0;
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+nn_count_kernel(const double *__restrict__ coords, long N, const unsigned long long *__restrict__ bounds, int G,
+                int *__restrict__ cell_of, int *__restrict__ counts) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const NnGrid g = nn_grid_of(bounds, G);
+    const int c = nn_cell_coord(coords[N + i], g.ymin, g.inv_hy, G) * G + nn_cell_coord(coords[i], g.xmin, g.inv_hx, G);
+    cell_of[i] = c;
+    atomicAdd(&counts[c], 1);
+}
+
+__global__ void __launch_bounds__(256)
+nn_scatter_kernel(const double *__restrict__ coords, long N, const int *__restrict__ cell_of,
+                  const int *__restrict__ offsets, int *__restrict__ fill, double2 *__restrict__ sorted_xy,
+                  int *__restrict__ sorted_id) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const int c = cell_of[i];
+    const int pos = offsets[c] + atomicAdd(&fill[c], 1);
+    sorted_xy[pos] = make_double2(coords[i], coords[N + i]);
+    sorted_id[pos] = (int)i;
+}
+
+__global__ void __launch_bounds__(128)
+nn_search_kernel(const double2 *__restrict__ sorted_xy, const int *__restrict__ sorted_id, long N,
+                 const int *__restrict__ offsets, const unsigned long long *__restrict__ bounds, int G,
+                 unsigned long long *__restrict__ nn) {
+    const long t = (long)blockIdx.x * 128 + threadIdx.x;
+    if (t >= N) return;
+    const NnGrid g = nn_grid_of(bounds, G);
+    const double2 me = sorted_xy[t];
+    const int pcx = nn_cell_coord(me.x, g.xmin, g.inv_hx, G), pcy = nn_cell_coord(me.y, g.ymin, g.inv_hy, G);
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    for (int r = 0;; ++r) {
+        const int x0 = pcx - r, x1 = pcx + r, y0 = pcy - r, y1 = pcy + r;
+        const int ya = y0 > 0 ? y0 : 0, yb = y1 < G - 1 ? y1 : G - 1;
+        const int xa = x0 > 0 ? x0 : 0, xb = x1 < G - 1 ? x1 : G - 1;
+        for (int uy = ya; uy <= yb; ++uy) {
+            const bool full_row = uy == y0 || uy == y1;
+            // a full row of the ring is one contiguous run of the sorted cells; inside rows
+            // contribute their two end cells
+            const int n_seg = full_row ? 1 : (r == 0 ? 1 : 2);
+            for (int seg = 0; seg < n_seg; ++seg) {
+                int ca, cb;
+                if (full_row) {
+                    ca = xa; cb = xb;
+                } else {
+                    const int ux = seg == 0 ? x0 : x1;
+                    if (ux < 0 || ux > G - 1) continue;
+                    ca = cb = ux;
+                }
+                const int qa = offsets[uy * G + ca], qb = offsets[uy * G + cb + 1];
+                for (int q = qa; q < qb; ++q) {
+                    if (q == t) continue;
+                    const double2 o = sorted_xy[q];
+                    const double dx = me.x - o.x, dy = me.y - o.y;
+                    const double d2 = fma(dx, dx, dy * dy);
+                    if (d2 < best) best = d2;
+                }
+            }
+        }
+        if (best == 0.0) break;
+        // distance to the border of the block searched so far; sides on the edge of the grid do not count
+        double bound = __longlong_as_double(0x7ff0000000000000LL);
+        if (x0 > 0) bound = fmin(bound, me.x - (g.xmin + x0 * g.hx));
+        if (x1 < G - 1) bound = fmin(bound, (g.xmin + (x1 + 1) * g.hx) - me.x);
+        if (y0 > 0) bound = fmin(bound, me.y - (g.ymin + y0 * g.hy));
+        if (y1 < G - 1) bound = fmin(bound, (g.ymin + (y1 + 1) * g.hy) - me.y);
+        if (!(bound < __longlong_as_double(0x7ff0000000000000LL))) break;       // the whole grid was searched
+        bound = fmax(bound, 0.0) * (1.0 - 1e-9);          // rounding of the cell borders
+        if (best <= bound * bound) break;
+    }
+    nn[sorted_id[t]] = dist_key(best);
 }
 
 __global__ void __launch_bounds__(256)
@@ -164,14 +309,6 @@ cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ 
 // r = +-2^14, so the full 32-bit weight meets the only non-zero digit.
 // range[0] = ordered key of min(v), range[1] = ordered key of max(v).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ordered_key(double v) {
-    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double from_ordered_key(unsigned long long key) {
-    const unsigned long long u = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
-    return __longlong_as_double((long long)u);
-}
 
 __global__ void __launch_bounds__(256)
 value_range_kernel(const double *__restrict__ values, long K, long N, long ld,
@@ -660,10 +797,13 @@ struct Plan {
     int sr;
     long nblk, Kpad, Npad;
     long slab_tiles;                             // cell tiles (128 cells i) whose weight planes are resident at once
+    int nn_grid;                                 // cells per side of the nearest-neighbour grid (0: brute force)
+    size_t nn_xy_off, nn_id_off, nn_cell_off, nn_cnt_off, nn_scan_off, nn_scan_bytes;
     size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, table_off, weights_off, total;
 };
 
 constexpr size_t kWeightSlabBudget = 6ull << 30;   // bytes of generated weight planes kept at a time
+constexpr long kGridNnMinCells = 4096;             // below this the brute-force nearest-neighbour kernel is as fast
 
 // FASTPROJECT_B200_SLAB_BYTES overrides the budget (tests use it to run many slabs at small N)
 size_t weight_slab_budget() {
@@ -717,6 +857,27 @@ bool make_plan(long N, long K, Plan *p) {
     off += 1024;
     p->table_off = off;
     off += align_up((size_t)TAB * TAB_COPIES * 8, 1024);
+    // nearest-neighbour grid: about one cell per grid cell; small projections keep the brute-force kernel
+    p->nn_grid = 0;
+    if (N >= kGridNnMinCells) {
+        int G = (int)ceil(sqrt((double)N));
+        if (G > 4096) G = 4096;
+        p->nn_grid = G;
+        const size_t cells = (size_t)G * G + 1;
+        p->nn_xy_off = off;
+        off += align_up((size_t)p->Npad * 16, 1024);
+        p->nn_id_off = off;
+        off += align_up((size_t)p->Npad * 4, 1024);
+        p->nn_cell_off = off;
+        off += align_up((size_t)p->Npad * 4, 1024);
+        p->nn_cnt_off = off;                     // counts | offsets | fill, `cells` ints each
+        off += align_up(3 * cells * 4, 1024);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int *)nullptr, (int *)nullptr, (int)cells);
+        p->nn_scan_bytes = scan_bytes;
+        p->nn_scan_off = off;
+        off += align_up(scan_bytes, 1024);
+    }
     p->slab_tiles = pick_slab_tiles(p->Npad / TN, p->nblk / 2, p->Npad);
     p->weights_off = off;
     off += align_up((size_t)WD * p->slab_tiles * TN * p->Npad, 1024);
@@ -810,13 +971,44 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         FP_CHECK_LAUNCH("pack_values_kernel");
     }
     {
-        FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // > +inf as a key
-        const unsigned bx = (unsigned)((N + 255) / 256);
-        unsigned by = (unsigned)((4 * fp::sm_count() + bx - 1) / bx);
-        if (by < 1) by = 1;
-        if ((long)by * 256 > N) by = (unsigned)((N + 255) / 256);
-        nearest_neighbour_kernel<<<dim3(bx, by), 256, 0, st>>>(coords, N, nn);
-        FP_CHECK_LAUNCH("nearest_neighbour_kernel");
+        // FASTPROJECT_B200_NN=brute: the O(N^2) kernel (tests compare the two)
+        const char *nn_env = getenv("FASTPROJECT_B200_NN");
+        const bool brute = nn_env && !strcmp(nn_env, "brute");
+        if (p.nn_grid && !brute) {
+            const int G = p.nn_grid;
+            const size_t cells = (size_t)G * G + 1;
+            double2 *sorted_xy = reinterpret_cast<double2 *>(ws + p.nn_xy_off);
+            int *sorted_id = reinterpret_cast<int *>(ws + p.nn_id_off);
+            int *cell_of = reinterpret_cast<int *>(ws + p.nn_cell_off);
+            int *counts = reinterpret_cast<int *>(ws + p.nn_cnt_off);
+            int *offsets = counts + cells, *fill = offsets + cells;
+            unsigned long long *bounds = range + 4;           // behind the value range in the flag block
+            FP_CHECK_CUDA(cudaMemsetAsync(bounds, 0xff, 16, st));
+            FP_CHECK_CUDA(cudaMemsetAsync(bounds + 2, 0, 16, st));
+            FP_CHECK_CUDA(cudaMemsetAsync(counts, 0, 3 * cells * 4, st));
+            FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // padding rows: > +inf as a key
+            const unsigned nb = (unsigned)((N + 255) / 256);
+            nn_bounds_kernel<<<nb < 1024 ? nb : 1024, 256, 0, st>>>(coords, N, bounds);
+            FP_CHECK_LAUNCH("nn_bounds_kernel");
+            nn_count_kernel<<<nb, 256, 0, st>>>(coords, N, bounds, G, cell_of, counts);
+            FP_CHECK_LAUNCH("nn_count_kernel");
+            size_t scan_bytes = p.nn_scan_bytes;
+            FP_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws + p.nn_scan_off, scan_bytes, counts, offsets, (int)cells, st));
+            fp::count_launch(1);
+            nn_scatter_kernel<<<nb, 256, 0, st>>>(coords, N, cell_of, offsets, fill, sorted_xy, sorted_id);
+            FP_CHECK_LAUNCH("nn_scatter_kernel");
+            nn_search_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(sorted_xy, sorted_id, N, offsets, bounds, G,
+                                                                         nn);
+            FP_CHECK_LAUNCH("nn_search_kernel");
+        } else {
+            FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // > +inf as a key
+            const unsigned bx = (unsigned)((N + 255) / 256);
+            unsigned by = (unsigned)((4 * fp::sm_count() + bx - 1) / bx);
+            if (by < 1) by = 1;
+            if ((long)by * 256 > N) by = (unsigned)((N + 255) / 256);
+            nearest_neighbour_kernel<<<dim3(bx, by), 256, 0, st>>>(coords, N, nn);
+            FP_CHECK_LAUNCH("nearest_neighbour_kernel");
+        }
         cell_setup_kernel<<<(unsigned)((p.Npad + 255) / 256), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N,
                                                                             p.Npad, nn, ci, cj,
                                                                             reinterpret_cast<double *>(ws + p.table_off));

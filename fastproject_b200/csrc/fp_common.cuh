@@ -52,37 +52,51 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 // interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then
 // a sequential tail; otherwise split at n/2 rounded down to a multiple of 8.
 // Reproduced so that row reductions (axis = contiguous axis) are bit-identical.
+// Written without recursion (explicit stack of pending halves): a recursive device function
+// needs stack the compiler cannot size, and overflows the default 1 KB per thread silently when
+// the caller's frame is large or the row is long.
 template <typename Load>
 __device__ double np_pairwise_sum(Load load, long lo, long n) {
-    if (n < 8) {
-        double res = -0.0;                   // NumPy starts the short loop from -0.0
-        for (long i = 0; i < n; i++) res = __dadd_rn(res, load(lo + i));
-        return res;
-    } else if (n <= 128) {
-        double r0 = load(lo + 0), r1 = load(lo + 1), r2 = load(lo + 2), r3 = load(lo + 3);
-        double r4 = load(lo + 4), r5 = load(lo + 5), r6 = load(lo + 6), r7 = load(lo + 7);
-        long i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-            r0 = __dadd_rn(r0, load(lo + i + 0));
-            r1 = __dadd_rn(r1, load(lo + i + 1));
-            r2 = __dadd_rn(r2, load(lo + i + 2));
-            r3 = __dadd_rn(r3, load(lo + i + 3));
-            r4 = __dadd_rn(r4, load(lo + i + 4));
-            r5 = __dadd_rn(r5, load(lo + i + 5));
-            r6 = __dadd_rn(r6, load(lo + i + 6));
-            r7 = __dadd_rn(r7, load(lo + i + 7));
+    long st_lo[40], st_n[40];
+    signed char st_seen[40];
+    double val[40];
+    int sp = 1, vp = 0;
+    st_lo[0] = lo; st_n[0] = n; st_seen[0] = 0;
+    while (sp) {
+        const long flo = st_lo[sp - 1], fn = st_n[sp - 1];
+        if (fn <= 128) {
+            double res;
+            if (fn < 8) {
+                res = -0.0;
+                for (long i = 0; i < fn; i++) res = __dadd_rn(res, load(flo + i));
+            } else {
+                double r[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = load(flo + k);
+                long i;
+                for (i = 8; i < fn - (fn % 8); i += 8) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], load(flo + i + k));
+                }
+                res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                for (; i < fn; i++) res = __dadd_rn(res, load(flo + i));
+            }
+            val[vp++] = res;
+            --sp;
+        } else if (!st_seen[sp - 1]) {
+            st_seen[sp - 1] = 1;
+            long n2 = fn / 2;
+            n2 -= n2 % 8;
+            st_lo[sp] = flo + n2; st_n[sp] = fn - n2; st_seen[sp] = 0; ++sp;     // right half: summed second
+            st_lo[sp] = flo; st_n[sp] = n2; st_seen[sp] = 0; ++sp;               // left half: summed first
+        } else {
+            const double b = val[--vp], a = val[--vp];
+            val[vp++] = __dadd_rn(a, b);
+            --sp;
         }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
-                               __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
-        for (; i < n; i++) res = __dadd_rn(res, load(lo + i));
-        return res;
-    } else {
-        long n2 = n / 2;
-        n2 -= n2 % 8;
-        double a = np_pairwise_sum(load, lo, n2);
-        double b = np_pairwise_sum(load, lo + n2, n - n2);
-        return __dadd_rn(a, b);
     }
+    return val[0];
 }
 
 // One leaf of that tree (8 <= n <= 128) summed by EIGHT consecutive lanes: lane k owns the

@@ -71,7 +71,11 @@ template <typename Load>
 __device__ double stats_tree_sum(Load load, const StatLeaf *leaves, int n_leaves, const int *prog, int n_prog,
                                  double *leaf_sum, double *bcast) {
     if (n_leaves == 1 && leaves[0].n < 8) {
-        if (threadIdx.x == 0) leaf_sum[0] = fp::np_pairwise_sum(load, leaves[0].lo, leaves[0].n);
+        if (threadIdx.x == 0) {                  // short loop, from -0.0 like NumPy's
+            double res = -0.0;
+            for (int i = 0; i < leaves[0].n; ++i) res = __dadd_rn(res, load(leaves[0].lo + i));
+            leaf_sum[0] = res;
+        }
     } else {
         const int per_pass = STATS_THREADS >> 3;
         for (int base = 0; base < n_leaves; base += per_pass) {

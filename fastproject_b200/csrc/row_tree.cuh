@@ -40,7 +40,11 @@ __device__ inline double fold_tree(const double *leaf_sum, const int *__restrict
 template <typename Load>
 __device__ __forceinline__ void leaf_sums(Load load, const Leaf *__restrict__ leaves, int n_leaves, double *leaf_sum) {
     if (n_leaves == 1 && leaves[0].n < 8) {
-        if (threadIdx.x == 0) leaf_sum[0] = fp::np_pairwise_sum(load, leaves[0].lo, leaves[0].n);
+        if (threadIdx.x == 0) {                  // short loop, from -0.0 like NumPy's
+            double res = -0.0;
+            for (int i = 0; i < leaves[0].n; ++i) res = __dadd_rn(res, load((long)leaves[0].lo + i));
+            leaf_sum[0] = res;
+        }
         return;
     }
     const int per_pass = blockDim.x >> 3;

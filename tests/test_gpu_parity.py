@@ -378,6 +378,38 @@ def test_tensor_core_weight_slabs_do_not_change_the_result(fp, n, k, budget, mon
     assert np.abs(a - one).max() <= 1e-7 * max(n, 16)
 
 
+@pytest.mark.parametrize("layout", ["blobs", "outliers", "duplicates", "line", "one_point_cloud"])
+def test_nearest_neighbour_grid_equals_brute_force(fp, layout, monkeypatch):
+    """The row scale of the tensor-core path is the nearest-neighbour distance of every cell.
+    From 4 096 cells on it comes from a uniform-grid search; it must be the brute-force kernel's
+    minimum exactly, so the whole output is BIT-IDENTICAL between the two."""
+    import torch
+    from scipy.stats import rankdata
+    rng = np.random.RandomState(21)
+    n, k = 6000, 5
+    if layout == "blobs":
+        xy = np.concatenate([rng.normal(c, s, size=(n // 4, 2)) for c, s in ((-1, .02), (0, .3), (.4, .05), (2, .2))])
+    elif layout == "outliers":
+        xy = rng.normal(0, 0.3, size=(n, 2)); xy[0] = [40.0, -35.0]; xy[1] = [-90.0, 2.0]
+    elif layout == "duplicates":
+        xy = rng.normal(0, 0.3, size=(n, 2)); xy[100:700] = xy[5]; xy[700:900] = xy[6]
+    elif layout == "line":
+        xy = np.stack([np.linspace(-1, 1, n), np.zeros(n)], axis=1)
+    else:
+        xy = np.tile([[0.25, -0.5]], (n, 1)); xy[:50] += rng.normal(0, 1e-3, size=(50, 2))
+    coords = torch.from_numpy(np.ascontiguousarray(xy.T)).cuda()
+    ld = fp.E.padded(n)
+    vals = torch.zeros((k, ld), dtype=torch.float64, device="cuda")
+    vals[:, :n] = torch.from_numpy(np.array([rankdata(rng.normal(size=n)) for _ in range(k)])).cuda()
+    grid = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="tc")[:, :n].cpu().numpy()
+    monkeypatch.setenv("FASTPROJECT_B200_NN", "brute")
+    brute = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="tc")[:, :n].cpu().numpy()
+    assert np.array_equal(grid, brute, equal_nan=True)
+    monkeypatch.delenv("FASTPROJECT_B200_NN")
+    ref = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="fp64")[:, :n].cpu().numpy()
+    assert np.abs(ref - grid).max() <= 1e-7 * n
+
+
 def test_tensor_core_kernel_binary_predictions(fp):
     a, b = _tc_case(fp, 2000, 300, 5, binary=True, kind=1)
     assert np.abs(a - b).max() <= 1e-8          # values in [0, 1]: the scale puts +-1 in the top digit
