@@ -145,16 +145,24 @@ struct NnGrid {
     double xmin, ymin, hx, hy, inv_hx, inv_hy;
 };
 
-// bounds[0..1]: ordered keys of min x, min y (initialised to all ones); [2..3]: max x, max y (zero)
+// bounds[0..1]: ordered keys of min x, min y (initialised to all ones); [2..3]: max x, max y
+// (zero); [4..7]: sums of x, x^2, y, y^2 as doubles (zero).  The grid covers mean +- 3 sigma of
+// each axis (clipped to the extremes): an outlier cell a thousand bandwidths away would
+// otherwise stretch the grid until the bulk of the cells shared a handful of grid cells.  Cells
+// outside the box fall into the border grid cells, whose outer sides never bound the search,
+// so the result does not depend on the box (nor on the order of the atomic sums).
 __global__ void __launch_bounds__(256)
 nn_bounds_kernel(const double *__restrict__ coords, long N, unsigned long long *__restrict__ bounds) {
     unsigned long long lo_x = ~0ull, lo_y = ~0ull, hi_x = 0ull, hi_y = 0ull;
+    double sx = 0.0, sxx = 0.0, sy = 0.0, syy = 0.0;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long)gridDim.x * 256) {
-        const unsigned long long kx = ordered_key(coords[i]), ky = ordered_key(coords[N + i]);
+        const double x = coords[i], y = coords[N + i];
+        const unsigned long long kx = ordered_key(x), ky = ordered_key(y);
         lo_x = kx < lo_x ? kx : lo_x;
         hi_x = kx > hi_x ? kx : hi_x;
         lo_y = ky < lo_y ? ky : lo_y;
         hi_y = ky > hi_y ? ky : hi_y;
+        sx += x; sxx += x * x; sy += y; syy += y * y;
     }
     for (int off = 16; off; off >>= 1) {
         unsigned long long o;
@@ -162,22 +170,43 @@ nn_bounds_kernel(const double *__restrict__ coords, long N, unsigned long long *
         o = __shfl_xor_sync(0xffffffffu, lo_y, off); lo_y = o < lo_y ? o : lo_y;
         o = __shfl_xor_sync(0xffffffffu, hi_x, off); hi_x = o > hi_x ? o : hi_x;
         o = __shfl_xor_sync(0xffffffffu, hi_y, off); hi_y = o > hi_y ? o : hi_y;
+        sx += __shfl_xor_sync(0xffffffffu, sx, off);
+        sxx += __shfl_xor_sync(0xffffffffu, sxx, off);
+        sy += __shfl_xor_sync(0xffffffffu, sy, off);
+        syy += __shfl_xor_sync(0xffffffffu, syy, off);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(&bounds[0], lo_x);
         atomicMin(&bounds[1], lo_y);
         atomicMax(&bounds[2], hi_x);
         atomicMax(&bounds[3], hi_y);
+        double *sums = reinterpret_cast<double *>(bounds + 4);
+        atomicAdd(&sums[0], sx);
+        atomicAdd(&sums[1], sxx);
+        atomicAdd(&sums[2], sy);
+        atomicAdd(&sums[3], syy);
     }
 }
 
-__device__ __forceinline__ NnGrid nn_grid_of(const unsigned long long *__restrict__ bounds, int G) {
+__device__ __forceinline__ void nn_axis(double vmin, double vmax, double s, double ss, long N, int G, double *lo,
+                                        double *h) {
+    const double mean = s / (double)N, var = ss / (double)N - mean * mean;
+    const double sd = var > 0.0 ? sqrt(var) : 0.0;
+    double a = fmax(vmin, mean - 3.0 * sd), b = fmin(vmax, mean + 3.0 * sd);
+    if (!(b > a)) {                                   // degenerate or non-finite: the extremes
+        a = vmin;
+        b = vmax;
+    }
+    const double w = b - a;
+    *lo = a;
+    *h = (w > 0.0 && w < 1.0e300) ? w / G : 1.0;
+}
+
+__device__ __forceinline__ NnGrid nn_grid_of(const unsigned long long *__restrict__ bounds, long N, int G) {
+    const double *sums = reinterpret_cast<const double *>(bounds + 4);
     NnGrid g;
-    g.xmin = from_ordered_key(bounds[0]);
-    g.ymin = from_ordered_key(bounds[1]);
-    const double wx = from_ordered_key(bounds[2]) - g.xmin, wy = from_ordered_key(bounds[3]) - g.ymin;
-    g.hx = wx > 0.0 ? wx / G : 1.0;
-    g.hy = wy > 0.0 ? wy / G : 1.0;
+    nn_axis(from_ordered_key(bounds[0]), from_ordered_key(bounds[2]), sums[0], sums[1], N, G, &g.xmin, &g.hx);
+    nn_axis(from_ordered_key(bounds[1]), from_ordered_key(bounds[3]), sums[2], sums[3], N, G, &g.ymin, &g.hy);
     g.inv_hx = 1.0 / g.hx;
     g.inv_hy = 1.0 / g.hy;
     return g;
@@ -194,7 +223,7 @@ nn_count_kernel(const double *__restrict__ coords, long N, const unsigned long l
                 int *__restrict__ cell_of, int *__restrict__ counts) {
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
-    const NnGrid g = nn_grid_of(bounds, G);
+    const NnGrid g = nn_grid_of(bounds, N, G);
     const int c = nn_cell_coord(coords[N + i], g.ymin, g.inv_hy, G) * G + nn_cell_coord(coords[i], g.xmin, g.inv_hx, G);
     cell_of[i] = c;
     atomicAdd(&counts[c], 1);
@@ -218,7 +247,7 @@ nn_search_kernel(const double2 *__restrict__ sorted_xy, const int *__restrict__ 
                  unsigned long long *__restrict__ nn) {
     const long t = (long)blockIdx.x * 128 + threadIdx.x;
     if (t >= N) return;
-    const NnGrid g = nn_grid_of(bounds, G);
+    const NnGrid g = nn_grid_of(bounds, N, G);
     const double2 me = sorted_xy[t];
     const int pcx = nn_cell_coord(me.x, g.xmin, g.inv_hx, G), pcy = nn_cell_coord(me.y, g.ymin, g.inv_hy, G);
     double best = __longlong_as_double(0x7ff0000000000000LL);
@@ -984,7 +1013,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
             int *offsets = counts + cells, *fill = offsets + cells;
             unsigned long long *bounds = range + 4;           // behind the value range in the flag block
             FP_CHECK_CUDA(cudaMemsetAsync(bounds, 0xff, 16, st));
-            FP_CHECK_CUDA(cudaMemsetAsync(bounds + 2, 0, 16, st));
+            FP_CHECK_CUDA(cudaMemsetAsync(bounds + 2, 0, 48, st));     // maxima and the four sums
             FP_CHECK_CUDA(cudaMemsetAsync(counts, 0, 3 * cells * 4, st));
             FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // padding rows: > +inf as a key
             const unsigned nb = (unsigned)((N + 255) / 256);
