@@ -19,6 +19,9 @@ METHODS = ("naive", "weighted_avg", "imputed", "only_nonzero")
 def gene_row_index(row_labels):
     """gene label -> row (int) or rows (list) if the label is duplicated.  The
     reference loop (:747-753) visits every row, so duplicates all match."""
+    index = dict(zip(row_labels, range(len(row_labels))))
+    if len(index) == len(row_labels):        # no duplicated label: the common case, one C-level pass
+        return index
     index = dict()
     for pos, gene in enumerate(row_labels):
         prev = index.get(gene)
