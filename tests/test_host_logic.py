@@ -167,3 +167,87 @@ def test_significance_filter_semantics():
     assert sum(1 for k in keep if keep[k] and not m["signatureScores"][k].isPrecomputed) <= 200
     m = model(3.0)
     assert all(P.filter_significant_signatures(m, n_samples=5000, all_sigs=True).values())
+
+
+def _grid_nearest_neighbour(x, y):
+    """Line-by-line Python model of nn_count / nn_search_kernel (csrc/consistency_tc.cu): grid over
+    mean +- 3 sigma clipped to the extremes, cells outside it in the border grid cells, Chebyshev
+    rings until the best distance is within the block searched so far."""
+    import math
+    n = len(x)
+    G = int(min(4096, math.ceil(math.sqrt(n))))
+
+    def axis(v):
+        mean, sd = v.mean(), v.std()
+        a, b = max(v.min(), mean - 3 * sd), min(v.max(), mean + 3 * sd)
+        if not b > a:
+            a, b = v.min(), v.max()
+        w = b - a
+        return a, (w / G if 0 < w < 1e300 else 1.0)
+    (xmin, hx), (ymin, hy) = axis(x), axis(y)
+
+    def coord(v, vmin, h):
+        t = (v - vmin) * (1.0 / h)
+        return np.clip(np.where(t >= G, G - 1, np.trunc(t)), 0, G - 1).astype(np.int64)
+    cx, cy = coord(x, xmin, hx), coord(y, ymin, hy)
+    cell = cy * G + cx
+    order = np.argsort(cell, kind="stable")
+    start = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=G * G))])
+    sx, sy = x[order], y[order]
+    out = np.full(n, np.inf)
+    for t in range(n):
+        px, py, pcx, pcy = sx[t], sy[t], cx[order[t]], cy[order[t]]
+        best, r = np.inf, 0
+        while True:
+            x0, x1, y0, y1 = pcx - r, pcx + r, pcy - r, pcy + r
+            for uy in range(max(0, y0), min(G - 1, y1) + 1):
+                if uy in (y0, y1):
+                    segs = [(max(0, x0), min(G - 1, x1))]
+                else:
+                    segs = [(u, u) for u in ((x0,) if r == 0 else (x0, x1)) if 0 <= u <= G - 1]
+                for ca, cb in segs:
+                    for q in range(start[uy * G + ca], start[uy * G + cb + 1]):
+                        if q != t:
+                            dx, dy = px - sx[q], py - sy[q]
+                            best = min(best, dx * dx + dy * dy)
+            if best == 0.0:
+                break
+            bound = np.inf
+            if x0 > 0:
+                bound = min(bound, px - (xmin + x0 * hx))
+            if x1 < G - 1:
+                bound = min(bound, (xmin + (x1 + 1) * hx) - px)
+            if y0 > 0:
+                bound = min(bound, py - (ymin + y0 * hy))
+            if y1 < G - 1:
+                bound = min(bound, (ymin + (y1 + 1) * hy) - py)
+            if not bound < np.inf:
+                break
+            bound = max(bound, 0.0) * (1.0 - 1e-9)
+            if best <= bound * bound:
+                break
+            r += 1
+        out[order[t]] = best
+    return out
+
+
+def test_nearest_neighbour_grid_search_rule():
+    """The ring-search termination rule and the outlier-proof grid box of the device kernels,
+    checked against the O(N^2) minimum on layouts that stress them (the kernels themselves are
+    compared with the brute-force kernel in tests/test_gpu_parity.py)."""
+    rng = np.random.RandomState(0)
+    layouts = [
+        (rng.uniform(-1, 1, 700), rng.uniform(-1, 1, 700)),
+        (np.concatenate([rng.normal(c, 0.02, 150) for c in (-1, 0, 0.3, 2)]),
+         np.concatenate([rng.normal(c, 0.03, 150) for c in (1, 0, -0.3, 2)])),
+        (np.r_[rng.normal(0, 0.3, 500), 900.0, -700.0], np.r_[rng.normal(0, 0.3, 500), -500.0, 600.0]),
+        (np.r_[rng.normal(0, 0.3, 300), np.zeros(50)], np.r_[rng.normal(0, 0.3, 300), np.zeros(50)]),
+        (np.linspace(0, 1, 300), np.zeros(300)),
+        (np.ones(40), np.ones(40)),
+        (np.array([0.0, 1.0, 10.0]), np.array([0.0, 0.0, 0.0])),
+    ]
+    for x, y in layouts:
+        x, y = np.asarray(x, float), np.asarray(y, float)
+        d = (x[:, None] - x[None, :]) ** 2 + (y[:, None] - y[None, :]) ** 2
+        np.fill_diagonal(d, np.inf)
+        assert np.array_equal(_grid_nearest_neighbour(x, y), d.min(axis=1))
