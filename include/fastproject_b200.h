@@ -18,7 +18,9 @@
  *     void*; NULL = legacy default stream); no hidden device allocation:
  *     scratch space is sized by the *_workspace_bytes() query and supplied by
  *     the caller;
- *   - matrices are row-major with an explicit leading dimension in ELEMENTS.
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - one CUDA device per process (the deployment is one process per GPU): kernel
+ *     attributes, the SM count and the resident-cluster count are cached per process.
  *
  * Device data layout
  *   expression X, weights W, zero mask Z : genes x cells, float64, ld >= N
