@@ -8,7 +8,7 @@
 // scipy.special.ndtr's branch structure (erf inside |x/sqrt2| < 1, erfc
 // outside).  sigma == 0 is NOT guarded, exactly as in the reference (:442):
 // the quotient becomes +-inf or NaN and the CDF follows IEEE rules.
-#include "fp_common.cuh"
+#include "row_tree.cuh"
 
 namespace {
 
@@ -35,37 +35,7 @@ struct GroupSquaredDev {
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_MAX_LEAVES = 1024;
 
-struct StatLeaf {
-    int lo, n;
-};
-
-__device__ void stats_build_tree(long lo, long n, StatLeaf *leaves, int *n_leaves, int *prog, int *n_prog) {
-    long st_lo[48], st_n[48];
-    int st_seen[48];
-    int sp = 0, nl = 0, np = 0;
-    st_lo[0] = lo; st_n[0] = n; st_seen[0] = 0; sp = 1;
-    while (sp) {
-        const long flo = st_lo[sp - 1], fn = st_n[sp - 1];
-        if (fn <= 128) {
-            prog[np++] = nl;
-            leaves[nl].lo = (int)flo;
-            leaves[nl].n = (int)fn;
-            ++nl;
-            --sp;
-        } else if (!st_seen[sp - 1]) {
-            st_seen[sp - 1] = 1;
-            long n2 = fn / 2;
-            n2 -= n2 % 8;
-            st_lo[sp] = flo + n2; st_n[sp] = fn - n2; st_seen[sp] = 0; ++sp;     // right half: visited second
-            st_lo[sp] = flo; st_n[sp] = n2; st_seen[sp] = 0; ++sp;               // left half: visited first
-        } else {
-            prog[np++] = -1;                     // both halves summed: add them
-            --sp;
-        }
-    }
-    *n_leaves = nl;
-    *n_prog = np;
-}
+using StatLeaf = fp::rowtree::Leaf;
 
 template <typename Load>
 __device__ double stats_tree_sum(Load load, const StatLeaf *leaves, int n_leaves, const int *prog, int n_prog,
@@ -126,7 +96,7 @@ background_stats_kernel(const double *__restrict__ rnd_med, const int32_t *__res
         }
         return;
     }
-    if (threadIdx.x == 0) stats_build_tree(lo, n, leaves, &n_leaves, prog, &n_prog);
+    if (threadIdx.x == 0) fp::rowtree::build_tree_device(lo, n, leaves, &n_leaves, prog, &n_prog);
     __syncthreads();
     const double mean = __ddiv_rn(stats_tree_sum(val, leaves, n_leaves, prog, n_prog, leaf_sum, &bcast), (double)n);
     GroupSquaredDev dev{rnd_med, rnd_order, mean};

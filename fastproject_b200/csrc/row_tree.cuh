@@ -57,6 +57,42 @@ __device__ __forceinline__ void leaf_sums(Load load, const Leaf *__restrict__ le
     }
 }
 
+// The same enumeration on the device (iterative: explicit stack of pending halves), so that the
+// tree reaches the kernels without a host -> device copy -- a copy-engine transfer would queue
+// behind whatever large upload is in flight, and its pageable source forces a stream sync.
+__device__ inline void build_tree_device(long lo, long n, Leaf *leaves, int *n_leaves, int *prog, int *n_prog) {
+    long st_lo[MAX_DEPTH], st_n[MAX_DEPTH];
+    signed char st_seen[MAX_DEPTH];
+    int sp = 1, nl = 0, np = 0;
+    st_lo[0] = lo; st_n[0] = n; st_seen[0] = 0;
+    while (sp) {
+        const long flo = st_lo[sp - 1], fn = st_n[sp - 1];
+        if (fn <= 128) {
+            prog[np++] = nl;
+            leaves[nl].lo = (int)flo;
+            leaves[nl].n = (int)fn;
+            ++nl;
+            --sp;
+        } else if (!st_seen[sp - 1]) {
+            st_seen[sp - 1] = 1;
+            long n2 = fn / 2;
+            n2 -= n2 % 8;
+            st_lo[sp] = flo + n2; st_n[sp] = fn - n2; st_seen[sp] = 0; ++sp;     // right half: visited second
+            st_lo[sp] = flo; st_n[sp] = n2; st_seen[sp] = 0; ++sp;               // left half: visited first
+        } else {
+            prog[np++] = -1;                     // both halves summed: add them
+            --sp;
+        }
+    }
+    if (n_leaves) *n_leaves = nl;
+    if (n_prog) *n_prog = np;
+}
+
+// one thread fills the leaf table and the program of rows of N elements in the workspace
+static __global__ void build_tree_kernel(long N, Leaf *leaves, int *prog) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) build_tree_device(0, N, leaves, nullptr, prog, nullptr);
+}
+
 inline void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
     if (depth > max_depth) max_depth = depth;
     if (n <= 128) {

@@ -141,9 +141,9 @@ extern "C" int fp_compute_weights(const double *X, const double *p_nd, const dou
     }
     cudaStream_t st = fp::as_stream(stream);
     char *ws = static_cast<char *>(workspace);
-    FP_CHECK_CUDA(cudaMemcpyAsync(ws, leaves.data(), leaves.size() * sizeof(Leaf), cudaMemcpyHostToDevice, st));
-    FP_CHECK_CUDA(cudaMemcpyAsync(ws + leaves_b, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    FP_CHECK_CUDA(cudaStreamSynchronize(st));          // the host vectors die at return
+    fp::rowtree::build_tree_kernel<<<1, 32, 0, st>>>(N, reinterpret_cast<Leaf *>(ws),
+                                                     reinterpret_cast<int *>(ws + leaves_b));
+    FP_CHECK_LAUNCH("build_tree_kernel");              // the host copy above only sized the tables
     static size_t smem_set = 0;
     if (smem > 40 * 1024 && smem > smem_set) {
         FP_CHECK_CUDA(cudaFuncSetAttribute(compute_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

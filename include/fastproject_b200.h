@@ -170,7 +170,9 @@ int fp_pull_host(void *dst_device, const void *src_pinned_host, size_t bytes, vo
  * std == 0 -> 1.  Replace NormalizationMethods.row_normalization (:34-41, the pipeline
  * default applied at Pipelines.py:202) and col_normalization (:24-31); the sums follow
  * NumPy's order (pairwise along rows, sequential along columns), so the output is
- * bit-identical to the reference.  out may not alias X.
+ * bit-identical to the reference.  out may not alias X.  The workspace of the row variant
+ * holds the pairwise-summation tree of rows of N elements (built on the device); the
+ * calls are asynchronous on the caller's stream.
  */
 size_t fp_normalize_rows_workspace_bytes(int64_t N);
 int fp_normalize_rows(const double *X, int64_t G, int64_t N, int64_t ld, double *out, int64_t ld_out,
