@@ -64,9 +64,13 @@ def calculate_sig_scores(data, signatures, method='weighted_avg',
     Returns dict name -> SignatureScores (insertion-ordered).  The score vectors
     stay on the GPU until ``.scores`` / ``.ranks`` is read.
 
-    ``distributed`` (extension): one process per GPU, every rank passes the SAME expression data
-    and ITS block of signatures; the matrices are then uploaded cooperatively (1/world of the
-    rows per PCIe link, all-gathered over NVLink)."""
+    ``distributed`` (extension): one process per GPU, ONE job -- every rank makes the same call
+    with the same data and the same signature list.  The matrices are uploaded cooperatively
+    (1/world of the rows per PCIe link, all-gathered over NVLink), a rank matches, packs and
+    scores its contiguous block of the signatures, and the returned dictionary names every kept
+    signature of the job; reading ``.scores`` / ``.ranks`` of any entry gathers the rows of all
+    ranks (a collective: every rank must do it), ``sigs_vs_projections(distributed=True)``
+    consumes them on the device."""
     if method not in _scoring.METHODS:
         # the reference leaves sig_score_method unbound here (UnboundLocalError)
         raise UnboundLocalError("unknown signature score method %r" % (method,))
@@ -212,18 +216,23 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     :param sig_scores_dict: dict of (string) => SignatureScores
     :param random_sig_scores_dict: dict of (string) => SignatureScores (background)
     :param NEIGHBORHOOD_SIZE: Gaussian kernel bandwidth (scalar, as in the reference)
-    :param precision: (extension) "fp64" | "tc"; default from
-        FASTPROJECT_B200_PRECISION, else "fp64"
+    :param precision: (extension) "auto" | "tc" | "fp64"; default from FASTPROJECT_B200_PRECISION,
+        else "auto": the tensor-core contraction (exact digit-sliced int8 products, 32-bit
+        fixed-point weights; every value must be a half-integer -- ranks, one-hot columns) and
+        the FP64 kernel for anything it refuses or does not cover.  "tc" raises instead of
+        falling back; "fp64" always uses the FP64 kernel.
     :param sigma_per_cell: (extension) optional (N,) array of per-cell bandwidths
         replacing NEIGHBORHOOD_SIZE
     :param prefetch_next: (extension) host matrices (expression, weights, ...) of the NEXT data
         set: their upload is started on a side stream once this call has uploaded its own small
         inputs, and overlaps the projection loop (see ``fastproject_b200.prefetch``)
-    :param distributed: (extension) one process per GPU (``torch.distributed`` initialised):
-        every rank passes ITS block of the signature dictionaries; the per-pair medians are
-        all-gathered (the only exchange), the random background pools all ranks, and every
-        rank returns the full result with rows in rank order -- what the reference would
-        return for the concatenated dictionaries
+    :param distributed: (extension) one process per GPU (``torch.distributed`` initialised), ONE
+        job: every rank passes the same projections and the dictionaries returned by
+        ``calculate_sig_scores(..., distributed=True)`` on the same signature lists.  The rank
+        rows are all-gathered over NVLink, the (projection x signature-block) grid is cut into
+        one run per rank (``distributed.partition_units``), the per-pair medians are summed
+        over the ranks (every entry has one owner), and every rank returns the full result --
+        what the reference returns for the same call
     :return: (sp_row_labels, sp_col_labels, sig_proj_matrix, sig_proj_matrix_p (log10 q),
               random_sig_proj_matrix, random_sig_score_keys)
     """
@@ -248,15 +257,17 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     N_RANDOM = len(random_sig_score_keys)
 
     dev = _engine.require_cuda()
+    world_size, rank = 1, 0
+    if distributed:
+        from . import distributed as D
+        world_size, rank = D.world()
     std_objs = [sig_scores_dict[k] for k in sp_row_labels]
     rnd_objs = [random_sig_scores_dict[k] for k in random_sig_score_keys]
-    ranks = _device_rank_rows(std_objs + rnd_objs, N_SAMPLES)           # :359-369
+    ranks = _device_rank_rows(std_objs + rnd_objs, N_SAMPLES)           # :359-369 (all rows, every rank)
+    n_rows = N_SIGNATURES + N_RANDOM
 
-    if distributed:
-        order = gptr = sig_group = np.zeros((0,), dtype=np.int32)       # grouped globally after the gather
-    else:
-        order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
-                                                    [o.numGenes for o in std_objs])
+    order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
+                                                [o.numGenes for o in std_objs])
     d_tables = _engine.to_device(np.concatenate([order, gptr, sig_group]).astype(np.int32), torch.int32)
     d_order = d_tables[:order.size]
     d_gptr = d_tables[order.size:order.size + gptr.size]
@@ -266,10 +277,6 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
         sig2 = _engine.to_device(np.asarray(sigma_per_cell, dtype=np.float64) ** 2)
     else:
         sig2 = NEIGHBORHOOD_SIZE ** 2                                   # :398
-
-    med_all = torch.empty((N_PROJECTIONS, N_SIGNATURES + N_RANDOM), dtype=torch.float64, device=dev)
-    p_all = torch.empty((N_PROJECTIONS, N_SIGNATURES), dtype=torch.float64, device=dev)
-    dissim = torch.empty_like(ranks)
 
     factor_sig_proj_matrix = np.zeros((len(sp_row_labels_factors), N_PROJECTIONS))
     factor_sig_proj_matrix_p = np.zeros((len(sp_row_labels_factors), N_PROJECTIONS))
@@ -288,62 +295,52 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     if prefetch_next is not None:
         _engine.prefetch(*prefetch_next, replicated=distributed)
 
-    for i, proj in enumerate(sp_col_labels):                            # :393
-        coords = coords_all[i]
-        if ranks.shape[0]:
-            # the rank matrix is the same for every projection: its digit planes are packed once
-            _engine.consistency(coords, sig2, ranks, N_SAMPLES, out=dissim, precision=precision,
-                                reuse_packed=i > 0, slot="svp")
-            med = _engine.row_medians(dissim, N_SAMPLES)                # :409, :414
-            med_all[i] = med
-            if N_SIGNATURES and not distributed:
-                p, _, _ = _engine.background_pvalues(med[:N_SIGNATURES], d_group,
-                                                     med[N_SIGNATURES:], d_order, d_gptr)   # :417-442
-                p_all[i] = p
+    # standard signatures, real and random together (:393-446): this rank's runs of the
+    # (projection x signature-block) grid -- on one GPU, every projection with all rows
+    if world_size > 1:
+        my_runs = D.partition_units(N_PROJECTIONS, n_rows, world_size)[rank]
+    else:
+        my_runs = [(i, 0, n_rows) for i in range(N_PROJECTIONS)] if n_rows else []
+    med_all = torch.zeros((N_PROJECTIONS, n_rows), dtype=torch.float64, device=dev)
+    if my_runs:
+        dissim = torch.empty((max(hi - lo for _, lo, hi in my_runs), ranks.shape[1]),
+                             dtype=torch.float64, device=dev)
+        _contract_runs(my_runs, coords_all, sig2, ranks, N_SAMPLES, dissim, med_all, precision)
+    if world_size > 1:
+        D.all_reduce_sum(med_all)                                       # the one exchange of stage 2
+    p_all = torch.empty((N_PROJECTIONS, N_SIGNATURES), dtype=torch.float64, device=dev)
+    if N_SIGNATURES:
+        for i in range(N_PROJECTIONS):
+            p, _, _ = _engine.background_pvalues(med_all[i, :N_SIGNATURES].contiguous(), d_group,
+                                                 med_all[i, N_SIGNATURES:].contiguous(), d_order,
+                                                 d_gptr)               # :417-442
+            p_all[i] = p
 
+    for i, proj in enumerate(sp_col_labels):
+        coords = coords_all[i]
         for j, sig in enumerate(sp_row_labels_pnum):                    # :451-481
-            cons, pval = _precomputed_numeric(sig_scores_dict[sig], coords, sig2, N_SAMPLES, precision)
+            # multi-GPU: the (signature, projection) pairs of this branch go round the ranks;
+            # every rank draws the permutation table (host RNG stream, cached by shape)
+            mine = (i * len(sp_row_labels_pnum) + j) % world_size == rank
+            cons, pval = _precomputed_numeric(sig_scores_dict[sig], coords, sig2, N_SAMPLES, precision,
+                                              compute=mine)
             pnum_sig_proj_matrix[j, i] = cons
             pnum_sig_proj_matrix_p[j, i] = pval
 
         for j, sig in enumerate(sp_row_labels_factors):                 # :484-518
+            # consumes the global NumPy stream: evaluated by every rank in the same order
             cons, pval = _factor(factor_dict[sig], coords, sig2, N_SAMPLES, precision)
             factor_sig_proj_matrix[j, i] = cons
             factor_sig_proj_matrix_p[j, i] = pval
 
-    if distributed:
-        # the one exchange of the multi-GPU path: medians (and the few host-side rows)
-        from . import distributed as D
-        import torch.distributed as dist
-        world_size, _ = D.world()
-        shape_all = D.all_gather_counts([N_SIGNATURES, N_SIGNATURES + N_RANDOM], device=dev).reshape(world_size, 2)
-        counts = [o.numGenes for o in std_objs] + [o.numGenes for o in rnd_objs]
-        counts_all = D.all_gather_counts(counts, device=dev)
-        bg = D.GlobalBackground(counts_all, [int(v) for v in shape_all[:, 0]],
-                                [int(v) for v in shape_all[:, 1]], dev)
-        gathered = D.all_gather_rows(med_all)
-        p_all = bg.pvalues(gathered) if len(bg.real_cols_host) else torch.empty(
-            (N_PROJECTIONS, 0), dtype=torch.float64, device=dev)
-        med_host = gathered.cpu().numpy()
-        sig_proj_matrix = 1 - med_host[:, bg.real_cols_host].T / N_SAMPLES
-        random_sig_proj_matrix = 1 - med_host[:, bg.rnd_cols_host].T / N_SAMPLES
-        small = [None] * world_size
-        dist.all_gather_object(small, dict(std=sp_row_labels, fac=sp_row_labels_factors,
-                                           pnum=sp_row_labels_pnum, rkeys=random_sig_score_keys,
-                                           fm=factor_sig_proj_matrix, fp=factor_sig_proj_matrix_p,
-                                           pm=pnum_sig_proj_matrix, pp=pnum_sig_proj_matrix_p))
-        sp_row_labels = [n for part in small for n in part["std"]]
-        sp_row_labels_factors = [n for part in small for n in part["fac"]]
-        sp_row_labels_pnum = [n for part in small for n in part["pnum"]]
-        random_sig_score_keys = [n for part in small for n in part["rkeys"]]
-        factor_sig_proj_matrix = np.concatenate([part["fm"] for part in small], axis=0)
-        factor_sig_proj_matrix_p = np.concatenate([part["fp"] for part in small], axis=0)
-        pnum_sig_proj_matrix = np.concatenate([part["pm"] for part in small], axis=0)
-        pnum_sig_proj_matrix_p = np.concatenate([part["pp"] for part in small], axis=0)
-    else:
-        med_host = med_all.cpu().numpy()
-        sig_proj_matrix = 1 - med_host[:, :N_SIGNATURES].T / N_SAMPLES      # :444
-        random_sig_proj_matrix = 1 - med_host[:, N_SIGNATURES:].T / N_SAMPLES   # :445
+    if world_size > 1 and sp_row_labels_pnum:
+        both = _engine.to_device(np.stack([pnum_sig_proj_matrix, pnum_sig_proj_matrix_p]))
+        both = D.all_reduce_sum(both).cpu().numpy()
+        pnum_sig_proj_matrix, pnum_sig_proj_matrix_p = both[0], both[1]
+
+    med_host = med_all.cpu().numpy()
+    sig_proj_matrix = 1 - med_host[:, :N_SIGNATURES].T / N_SAMPLES      # :444
+    random_sig_proj_matrix = 1 - med_host[:, N_SIGNATURES:].T / N_SAMPLES   # :445
     sig_proj_matrix_p = p_all.cpu().numpy().T.copy()
 
     sig_proj_matrix = np.concatenate((sig_proj_matrix, factor_sig_proj_matrix,
@@ -361,6 +358,42 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             random_sig_proj_matrix, random_sig_score_keys)
 
 
+def _contract_runs(runs, coords_all, sig2, ranks, n, dissim, med_all, precision):
+    """med_all[p, lo:hi] = median over cells of |rank - neighbourhood prediction| for every
+    run (projection p, rows lo..hi) -- :396-414.  The tensor-core mode refuses values it
+    cannot represent exactly; "auto" then repeats the run on the FP64 kernel, "tc" raises."""
+    requested = precision or _engine.default_precision()
+    pending = None                      # (rows view, indices of the runs launched on that shape)
+    todo = list(range(len(runs)))
+
+    def settle(batch):
+        view, idxs = batch
+        if _engine.consistency_refused(view, n, precision=requested, slot="svp"):
+            if requested != "auto":
+                raise _native.NativeError(
+                    "sigs_vs_projections(precision=%r): the values are not exactly representable on the "
+                    "tensor-core path (NaN / inf ranks, non-half-integers or too wide a range); use "
+                    "precision='fp64' or 'auto'" % (requested,))
+            for r in idxs:
+                p, lo, hi = runs[r]
+                dis = _engine.consistency(coords_all[p], sig2, ranks[lo:hi], n, out=dissim[:hi - lo],
+                                          precision="fp64", slot="svp")
+                med_all[p, lo:hi] = _engine.row_medians(dis, n)
+
+    for r in todo:
+        p, lo, hi = runs[r]
+        view = ranks[lo:hi]
+        if pending is not None and pending[0].shape[0] != view.shape[0]:
+            settle(pending)             # the flag lives in a workspace laid out for that shape
+            pending = None
+        dis = _engine.consistency(coords_all[p], sig2, view, n, out=dissim[:hi - lo],
+                                  precision=requested, slot="svp")
+        med_all[p, lo:hi] = _engine.row_medians(dis, n)
+        pending = (view, (pending[1] if pending else []) + [r])
+    if pending is not None:
+        settle(pending)
+
+
 def _single_group_pvalue(med_value, bg_medians):
     """p = Phi((m - mean(bg)) / std(bg)) on the device; sigma == 0 -> caller decides."""
     dev = bg_medians.device
@@ -372,15 +405,18 @@ def _single_group_pvalue(med_value, bg_medians):
     return float(p[0]), float(sd[0])
 
 
-def _precomputed_numeric(sig_scores, coords, sig2, n, precision):
+def _precomputed_numeric(sig_scores, coords, sig2, n, precision, compute=True):
     """Precomputed numerical signature vs one projection (:451-481): same
     dissimilarity; background = 10 000 column permutations of the rank vector
-    (host RNG stream of get_bg_dist) pushed through the same device kernels."""
+    (host RNG stream of get_bg_dist) pushed through the same device kernels.
+    ``compute=False`` (another rank owns this pair): only the host RNG side effects."""
     r = np.asarray(sig_scores.ranks, dtype=np.float64)
     if (r == r[0]).all():
-        return 0.0, 1.0
+        return (0.0, 1.0) if compute else (0.0, 0.0)
     NUM_REPLICATES = 10000
     perm = get_bg_dist(n, NUM_REPLICATES)                # (n, R) row indices
+    if not compute:
+        return 0.0, 0.0
     dev = coords.device
     ld = _engine.padded(n)
     r_dev = _engine.to_device(r)

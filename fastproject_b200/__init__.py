@@ -17,11 +17,24 @@ __all__ = ["SigScoreMethods", "Signatures", "NormalizationMethods", "Transforms"
 
 
 def prefetch(*arrays, **kw):
-    """Start the host -> device upload of expression / weight / zero-mask matrices on a side
-    stream; ``Signatures.calculate_sig_scores`` on the same arrays then finds them resident.
-    Overlaps the upload of the next data set with the kernels of the current one."""
+    """Declare host expression / weight / zero-mask matrices resident and start their upload on
+    a side stream; ``Signatures.calculate_sig_scores`` on the same array objects then uses the
+    device copies (until ``evict``).  Overlaps the upload of the next data set with the kernels
+    of the current one.  Nothing is kept resident without such a declaration."""
     from . import _engine
     _engine.prefetch(*arrays, **kw)
+
+
+def evict(*arrays):
+    """Release the resident device copies declared with ``prefetch``."""
+    from . import _engine
+    _engine.evict(*arrays)
+
+
+def resident(*arrays, **kw):
+    """Context manager: the matrices stay in HBM for every scoring call inside the block."""
+    from . import _engine
+    return _engine.resident(*arrays, **kw)
 
 
 def __getattr__(name):

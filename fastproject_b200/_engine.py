@@ -181,73 +181,60 @@ def to_host(dev_tensor):
 
 
 class _ExpressionCache(object):
-    """Keeps the last few genes x cells matrices resident in HBM so that the
-    two calculate_sig_scores calls of the pipeline (real, then random
-    signatures; Pipelines.py:204,229) upload X and W once.  An entry is reused
-    only if the host array has the same address, shape, strides and a matching
-    fingerprint (corner + strided samples); set FASTPROJECT_B200_NO_CACHE=1 to
-    disable."""
+    """Explicit residency of genes x cells host matrices in HBM.
 
-    def __init__(self, capacity=6):
+    Nothing is cached implicitly: a host matrix handed to ``calculate_sig_scores`` is
+    uploaded by that call and dropped with it, unless the caller has declared it resident --
+    ``fastproject_b200.prefetch(x, w, ...)`` (asynchronous upload, stays until ``evict``) or
+    the ``fastproject_b200.resident(x, w, ...)`` context manager.  The declaration is the
+    caller's promise that the host array is not modified while it is resident; entries are
+    found by the identity of the array object (the object is kept alive, so its address
+    cannot be recycled) plus its data pointer, shape, strides and dtype.  (Round 1 guessed
+    identity from the address and ~4 000 sampled elements, which missed in-place edits and
+    recycled addresses.)  In a multi-process run every rank must make the same declarations:
+    a replicated upload contains a collective."""
+
+    def __init__(self, capacity=8):
         self.capacity = capacity
-        self.entries = []          # list of (key, fingerprint, tensor)
+        self.entries = []          # list of [key, host object, device tensor, ready event | None]
 
     @staticmethod
     def _key(a):
         if isinstance(a, torch.Tensor):
-            return ("t", a.data_ptr(), tuple(a.shape), tuple(a.stride()), str(a.dtype), str(a.device))
-        a = np.asarray(a)
-        return ("n", a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+            return ("t", id(a), a.data_ptr(), tuple(a.shape), tuple(a.stride()), str(a.dtype))
+        if not isinstance(a, np.ndarray):
+            return None
+        return ("n", id(a), a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
 
-    @staticmethod
-    def _fingerprint(a):
-        if isinstance(a, torch.Tensor):
-            if a.is_cuda:
-                return None
-            a = a.numpy()
-        a = np.asarray(a)
-        flat_n = a.size
-        if flat_n == 0:
-            return b""
-        step = max(1, flat_n // 4099)
-        idx = np.arange(0, flat_n, step, dtype=np.int64)
-        sample = a.reshape(-1)[idx] if a.flags["C_CONTIGUOUS"] else a.T.reshape(-1)[idx]
-        return np.ascontiguousarray(sample).tobytes()
-
-    def _find(self, key, fp):
+    def _find(self, key):
+        if key is None:
+            return -1
         for i, entry in enumerate(self.entries):
-            if entry[0] == key and entry[1] == fp:
+            if entry[0] == key:
                 return i
         return -1
 
     def get(self, a, replicated=False):
-        """``replicated``: every rank of the process group holds the same host matrix (the
-        expression data of a multi-GPU run); each rank then uploads 1/world of the rows over
-        its own PCIe link and the rows are all-gathered over NVLink."""
-        upload = to_device_replicated if replicated else to_device
+        """Device copy of ``a``: the resident one if the caller declared it, else a fresh
+        upload that nobody remembers.  ``replicated``: every rank of the process group holds
+        the same host matrix; each rank then uploads 1/world of the rows over its own PCIe
+        link and the rows are all-gathered over NVLink."""
         if isinstance(a, torch.Tensor) and a.is_cuda:
             return a.to(torch.float64).contiguous()
-        if os.environ.get("FASTPROJECT_B200_NO_CACHE"):
-            return upload(a)
-        key, fp = self._key(a), self._fingerprint(a)
-        i = self._find(key, fp)
+        i = self._find(self._key(a))
         if i >= 0:
-            entry = self.entries.pop(i)
-            if entry[3] is not None:                 # prefetched on the copy stream: order after it
+            entry = self.entries[i]
+            if entry[3] is not None:                 # uploaded on the copy stream: order after it
                 torch.cuda.current_stream().wait_event(entry[3])
-                entry = (entry[0], entry[1], entry[2], None)
-            self.entries.append(entry)
+                entry[3] = None
             return entry[2]
-        t = upload(a)
-        self.entries.append((key, fp, t, None))
-        while len(self.entries) > self.capacity:
-            self.entries.pop(0)
-        return t
+        return (to_device_replicated if replicated else to_device)(a)
 
     def prefetch(self, a, replicated=False):
-        """Start the upload of a host matrix on a side stream and return at once; a later
-        ``get`` of the same array waits for the copy instead of issuing it.  Lets the upload of
-        the NEXT data set overlap the kernels of the current one (pinned host memory).
+        """Declare a host matrix resident and start its upload on a side stream; returns at
+        once.  A later ``get`` of the same array object waits for the copy instead of issuing
+        one.  Lets the upload of the NEXT data set overlap the kernels of the current one
+        (pinned host memory).
 
         The host -> device copy engine serves transfers in submission order (measured: the
         kilobyte-sized uploads of a running step -- index tables, coordinates -- waited ~90 ms
@@ -258,13 +245,16 @@ class _ExpressionCache(object):
         if isinstance(a, torch.Tensor) and a.is_cuda:
             return
         dev = require_cuda()
-        key, fp = self._key(a), self._fingerprint(a)
-        if self._find(key, fp) >= 0:
+        key = self._key(a)
+        if key is None:
+            raise TypeError("prefetch / resident need a NumPy array or a torch tensor (the object itself "
+                            "identifies the resident copy), got %r" % type(a))
+        if self._find(key) >= 0:
             return
         if isinstance(a, torch.Tensor):
             host = a
         else:
-            arr = np.asarray(a)
+            arr = a
             if arr.dtype == np.bool_:
                 arr = arr.astype(np.float64)
             if not arr.flags["C_CONTIGUOUS"]:
@@ -287,13 +277,12 @@ class _ExpressionCache(object):
             done = torch.cuda.Event()
             done.record(_copy_stream)
         t.record_stream(torch.cuda.current_stream())
-        self.entries.append((key, fp, t, done))
+        self.entries.append([key, a, t, done])
         while len(self.entries) > self.capacity:
             self.entries.pop(0)
 
     def evict(self, a):
-        key, fp = self._key(a), self._fingerprint(a)
-        i = self._find(key, fp)
+        i = self._find(self._key(a))
         if i >= 0:
             self.entries.pop(i)
 
@@ -306,12 +295,40 @@ expression_cache = _ExpressionCache()
 
 
 def prefetch(*arrays, **kw):
-    """Public hook: start uploading host matrices (expression, weights, zero mask) that a later
-    ``calculate_sig_scores`` call will use.  ``replicated=True``: the cooperative multi-GPU
-    upload (same arrays on every rank; every rank must make the same call)."""
+    """Public hook: declare host matrices (expression, weights, zero mask) resident and start
+    uploading them; later ``calculate_sig_scores`` calls on the same array OBJECTS use the
+    device copy.  The caller must not modify the arrays until ``evict`` (or ``resident``'s
+    exit).  ``replicated=True``: the cooperative multi-GPU upload (same arrays on every rank;
+    every rank must make the same call)."""
     for a in arrays:
         if a is not None:
             expression_cache.prefetch(a, kw.get("replicated", False))
+
+
+def evict(*arrays):
+    """Drop the resident device copies of these host matrices."""
+    for a in arrays:
+        if a is not None:
+            expression_cache.evict(a)
+
+
+class resident(object):
+    """``with fastproject_b200.resident(data.base, data.weights, zero_locations): ...`` -- the
+    matrices are uploaded once for all scoring calls inside the block (the pipeline scores the
+    real and the random signatures on the same data, Pipelines.py:204,229) and released at
+    its end."""
+
+    def __init__(self, *arrays, **kw):
+        self.arrays = [a for a in arrays if a is not None]
+        self.kw = kw
+
+    def __enter__(self):
+        prefetch(*self.arrays, **self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        evict(*self.arrays)
+        return False
 
 
 def clear_device_cache():
@@ -384,10 +401,10 @@ def normalize_cols(x):
 
 
 def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_ABS_ERROR,
-                precision=None, reuse_packed=False, slot="default"):
+                precision=None, slot="default"):
     """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor.
-    ``reuse_packed``: the previous call on the same workspace ``slot`` had the same
-    ``ranks`` (another projection): the tensor-core path skips re-packing them."""
+    Asynchronous.  The tensor-core mode refuses values it cannot represent exactly (the output
+    is then NaN): ``consistency_refused`` tells, after the calls on a workspace ``slot``."""
     k, ld = ranks.shape
     if out is None:
         out = torch.empty((k, ld), dtype=torch.float64, device=ranks.device)
@@ -396,11 +413,28 @@ def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_AB
     scalar = 0.0 if vec is not None else float(sigma_sq)
     nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
     ws, ws_ptr = _workspace(nbytes, ranks.device, slot)
-    if reuse_packed and mode == _native.PRECISION_CODES["tc"]:
-        output_kind |= _native.REUSE_PACKED
     _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
                  ptr(out), out.stride(0), output_kind, mode, ws_ptr, nbytes, stream_ptr())
     return out
+
+
+def consistency_refused(ranks, n, precision=None, slot="default"):
+    """True if the last ``consistency`` call on this workspace ``slot`` (same shape, same
+    precision) refused its values -- FP_PRECISION_TC holds half-integers of bounded range
+    only.  Synchronises the stream (call it once, after the projection loop)."""
+    k = ranks.shape[0]
+    mode = _native.PRECISION_CODES[resolve_precision(precision, n)]
+    if not k or mode != _native.PRECISION_CODES["tc"]:
+        return False
+    nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
+    ws, ws_ptr = _workspace(nbytes, ranks.device, slot)
+    rc = _native.load().fp_consistency_status(ws_ptr, n, k, mode, stream_ptr())
+    if rc == _native.FP_EUNSUPPORTED:
+        return True
+    if rc != 0:
+        raise _native.NativeError("fp_consistency_status failed (%d): %s"
+                                  % (rc, (_native.load().fp_last_error() or b"").decode()))
+    return False
 
 
 _WS_ALIGN = 1024

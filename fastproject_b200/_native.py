@@ -36,6 +36,7 @@ SIGNATURES = {
     "fp_consistency_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
     "fp_consistency": (c_int, [c_ptr, c_ptr, c_f64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64,
                                c_int, c_int, c_ptr, c_size, c_ptr]),
+    "fp_consistency_status": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr]),
     "fp_compute_weights_workspace_bytes": (c_size, [c_i64]),
     "fp_compute_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr,
                                    c_size, c_ptr]),
@@ -48,8 +49,8 @@ SIGNATURES = {
 METHOD_CODES = {"naive": 0, "weighted_avg": 1, "imputed": 2, "only_nonzero": 3}
 PRECISION_CODES = {"fp64": 0, "tc": 1}
 OUT_ABS_ERROR, OUT_PREDICTION = 0, 1
-REUSE_PACKED = 0x100
 RANK_AVERAGE, RANK_MIN = 0, 1
+FP_EUNSUPPORTED = -4
 
 _lib = None
 

@@ -12,6 +12,7 @@ int fp_consistency_fp64(const double *coords, const double *sigma_sq, double sig
                         int64_t ld_out, int output_kind, cudaStream_t st);
 
 size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K);
+int fp_consistency_tc_status(const void *workspace, int64_t N, int64_t K, cudaStream_t st);
 int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
                       const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
                       int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st);
@@ -65,13 +66,12 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
                  "fp_consistency: bad shape N=%ld K=%ld ld=%ld ld_out=%ld", (long)N, (long)K, (long)ld,
                  (long)ld_out);
     FP_CHECK_ARG(sigma_sq || sigma_sq_scalar > 0.0, "fp_consistency: sigma_sq must be positive");
-    FP_CHECK_ARG((output_kind & ~FP_REUSE_PACKED) == FP_OUT_ABS_ERROR ||
-                     (output_kind & ~FP_REUSE_PACKED) == FP_OUT_PREDICTION,
+    FP_CHECK_ARG(output_kind == FP_OUT_ABS_ERROR || output_kind == FP_OUT_PREDICTION,
                  "fp_consistency: unknown output kind %d", output_kind);
     if (K == 0) return FP_OK;
     if (precision_mode == FP_PRECISION_FP64)
         return fp_consistency_fp64(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim,
-                                   ld_out, output_kind & ~FP_REUSE_PACKED, fp::as_stream(stream));
+                                   ld_out, output_kind, fp::as_stream(stream));
     if (precision_mode == FP_PRECISION_TC)
         return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim, ld_out,
                                  output_kind, workspace, workspace_bytes, fp::as_stream(stream));
@@ -105,4 +105,15 @@ extern "C" int fp_pull_host(void *dst_device, const void *src_pinned_host, size_
         static_cast<uint4 *>(dst_device), static_cast<const uint4 *>(src_pinned_host), n16, bytes % 16);
     FP_CHECK_LAUNCH("pull_host_kernel");
     return FP_OK;
+}
+
+extern "C" int fp_consistency_status(const void *workspace, int64_t N, int64_t K, int precision_mode,
+                                     void *stream) {
+    fp::clear_error();
+    if (precision_mode != FP_PRECISION_TC) {
+        FP_CHECK_CUDA(cudaStreamSynchronize(fp::as_stream(stream)));
+        return FP_OK;
+    }
+    FP_CHECK_ARG(workspace && N > 0 && K > 0, "fp_consistency_status: bad arguments");
+    return fp_consistency_tc_status(workspace, N, K, fp::as_stream(stream));
 }

@@ -49,8 +49,9 @@
 // The FP64 verifier lives in consistency_fp64.cu.
 //
 // Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
-// slabs at small N); FP_TC_DBG=1 (timing experiments only, results are wrong with it set: the
-// MMAs are not issued).
+// slabs at small N).  No run-time switch changes the arithmetic: the "loads only" timing
+// experiment of round 1 is a compile-time option (-DFP_TC_TIMING_NO_MMA), never part of a
+// release build.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -575,7 +576,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                        const double *__restrict__ values, long ld, double *__restrict__ out, long ld_out, long N,
                        long K, long Kpad, long i_first, long plane_rows, int n_sig_pairs, int n_items,
                        int n_stages, int chunk_stages, int output_kind,
-                       const unsigned long long *__restrict__ range, const int *__restrict__ flag, int dbg) {
+                       const unsigned long long *__restrict__ range, const int *__restrict__ flag) {
     using L = MmaSmem<SR>;
     constexpr int STAGES = L::stages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -664,17 +665,17 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     if (elect_one()) {
                         const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
                         const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
-                        if (!(dbg & 1)) {
-                            // K step ks: 32 bytes further along the swizzled rows of both operands
-                            if (chunk_first)
-                                issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
-                            else
-                                issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
+#ifndef FP_TC_TIMING_NO_MMA
+                        // K step ks: 32 bytes further along the swizzled rows of both operands
+                        if (chunk_first)
+                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
+                        else
+                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
 #pragma unroll
-                            for (int ks = 1; ks < KS / 32; ++ks)
-                                issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2),
-                                                        idesc);
-                        }
+                        for (int ks = 1; ks < KS / 32; ++ks)
+                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2),
+                                                    idesc);
+#endif
                         umma_commit_pair(&empty[s]);          // frees the stage in both CTAs
                         if (chunk_last) umma_commit_pair(accum_full);
                     }
@@ -951,6 +952,24 @@ size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K) {
     return p.total;
 }
 
+int fp_consistency_tc_status(const void *workspace, int64_t N, int64_t K, cudaStream_t st) {
+    Plan p;
+    if (!make_plan(N, K, &p)) {
+        fp::set_error("fp_consistency_status: FP_PRECISION_TC supports N <= 4000000 cells (N=%ld)", (long)N);
+        return FP_EUNSUPPORTED;
+    }
+    int flag = 0;
+    FP_CHECK_CUDA(cudaMemcpyAsync(&flag, static_cast<const char *>(workspace) + p.flag_off, sizeof(int),
+                                  cudaMemcpyDeviceToHost, st));
+    FP_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        fp::set_error("fp_consistency: FP_PRECISION_TC refused the values (NaN / inf, not half-integers, or a "
+                      "range wider than three base-256 digits); every output of that call is NaN");
+        return FP_EUNSUPPORTED;
+    }
+    return FP_OK;
+}
+
 int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
                       const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
                       int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -980,10 +999,10 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
 
     unsigned long long *range = reinterpret_cast<unsigned long long *>(ws + p.range_off);
     unsigned long long *nn = reinterpret_cast<unsigned long long *>(ws + p.nn_off);
-    const bool reuse_packed = (output_kind & FP_REUSE_PACKED) != 0;
-    output_kind &= ~FP_REUSE_PACKED;
-    if (!reuse_packed) {
-        // value range and digit planes depend on the values only, not on the projection
+    {
+        // value range and digit planes: re-derived from `values` on every call.  (Round 1 had a
+        // caller-asserted "same values as the previous call" flag that skipped this; a wrong
+        // assertion gave silently wrong results, and verifying it costs as much as packing.)
         FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
         FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
         FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
@@ -1058,7 +1077,6 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         }
     }
     const int n_stages = (int)(p.Npad / KS);
-    const int dbg = getenv("FP_TC_DBG") ? atoi(getenv("FP_TC_DBG")) : 0;
     static bool attr_set = false;
     if (!attr_set) {
         FP_CHECK_CUDA(cudaFuncSetAttribute(consistency_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1099,11 +1117,11 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         if (p.sr == 2)
             consistency_mma_kernel<2><<<grid, THREADS, MmaSmem<2>::total, st>>>(
                 tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
-                n_stages, n_stages, output_kind, range, flag, dbg);
+                n_stages, n_stages, output_kind, range, flag);
         else
             consistency_mma_kernel<3><<<grid, THREADS, MmaSmem<3>::total, st>>>(
                 tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
-                n_stages, CHUNK_STAGES_3, output_kind, range, flag, dbg);
+                n_stages, CHUNK_STAGES_3, output_kind, range, flag);
         FP_CHECK_LAUNCH("consistency_mma_kernel");
     }
     return FP_OK;

@@ -1,24 +1,39 @@
 # -*- coding: utf-8 -*-
-"""Multi-GPU partitioning of the scoring core: one process per GPU, the
-signature rows (real + random background) are split into contiguous blocks,
-one block per rank.  Scoring, ranking, the neighbourhood contraction and the
-medians of a block need nothing from the other blocks, so the data path has no
-collective.  The only exchange is the all-gather of the per-(projection,
-signature) median dissimilarities -- O(signatures x projections) doubles --
-which every rank needs because the background N(mu, sigma) of a numGenes group
-(/root/reference/FastProject/Signatures.py:417-430) pools the random
-signatures of ALL blocks.
+"""Multi-GPU partitioning of the scoring core: one process per GPU, ONE job.
 
-The reference has no counterpart (it is single-process); the functions below
-only decide who owns which rows and put the gathered medians back into the
-reference's row order.  They work on any ``torch.distributed`` backend (NCCL
-on the GPUs, gloo in the CPU tests).
+Every rank is handed the same inputs (expression data, the full signature lists, all
+projections) and returns the same result as a single-GPU run; the work of the job is split:
+
+  stage 1  scoring + ranking : the kept signatures (real and random background alike) are cut
+           into contiguous, balanced row blocks, one per rank (``shard_bounds``).  A rank
+           reads X / W once and writes only its rows.
+  exchange ``all_gather_row_blocks``: the rank rows (float64 [rows x cells]) are all-gathered
+           over NVLink so that every rank can contract any block of signatures against any
+           projection (C2: 560 MB, C3 with 4 000 signatures: 3.2 GB per GPU).
+  stage 2  consistency + medians : the (projection x signature-block) grid -- blocks of 254
+           signatures, the row tile of one CTA pair of the tensor-core kernel -- is laid out
+           projection-major and cut into ``world`` contiguous runs (``partition_units``).  When
+           the number of projections is a multiple of the number of GPUs (C3: 8 / 8) a rank
+           owns whole projections and generates each projection's weight planes exactly once
+           in the job; otherwise (C2: 6 projections on 8 GPUs) a run straddles at most two
+           projections.
+  gather   ``all_reduce_sum`` of the [projections x signatures] medians, zero outside a rank's
+           own units (every entry has exactly one owner, so the sum is exact) -- C3: 256 KB.
+           The background N(mu, sigma) of a numGenes group pools random signatures of every
+           block (/root/reference/FastProject/Signatures.py:417-430), so every rank needs all
+           medians; p-values are then computed on every rank.
+
+The reference has no counterpart (it is single-process).  The helpers work on any
+``torch.distributed`` backend: NCCL on the GPUs; gloo in the CPU tests and in the
+two-ranks-on-one-GPU parity test, where CUDA tensors are staged through the host.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+SIG_BLOCK = 254          # signatures per CTA pair of consistency_mma_kernel (2 x 127)
 
 
 def world():
@@ -35,91 +50,82 @@ def shard_bounds(n_rows, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def all_gather_rows(local, n_rows_total=None, group=None):
-    """local: [P x rows_local] tensor of this rank's block ->
-    [P x rows_total] with the blocks in rank order.  Blocks may have unequal
-    widths (they are padded to the widest for the collective)."""
-    world_size, rank = world()
-    if world_size == 1:
-        return local
-    widths = torch.tensor([local.shape[1]], dtype=torch.int64, device=local.device)
-    all_w = [torch.zeros_like(widths) for _ in range(world_size)]
-    dist.all_gather(all_w, widths, group=group)
-    all_w = [int(w[0]) for w in all_w]
-    wmax = max(all_w)
-    padded = local
-    if local.shape[1] != wmax:
-        padded = torch.zeros((local.shape[0], wmax), dtype=local.dtype, device=local.device)
-        padded[:, :local.shape[1]] = local
-    padded = padded.contiguous()
-    parts = [torch.empty_like(padded) for _ in range(world_size)]
-    dist.all_gather(parts, padded, group=group)
-    out = torch.cat([p[:, :w] for p, w in zip(parts, all_w)], dim=1)
-    if n_rows_total is not None and out.shape[1] != n_rows_total:
-        raise RuntimeError("gathered %d rows, expected %d" % (out.shape[1], n_rows_total))
+def partition_units(n_proj, n_rows, world_size, block=SIG_BLOCK):
+    """(projection x signature-block) units, projection-major, cut into ``world_size``
+    contiguous runs of (nearly) equal length.  Returns, per rank, a list of
+    ``(projection, row_lo, row_hi)`` -- the units of one projection merged into one row range,
+    so a rank calls the contraction once per projection it touches."""
+    n_proj, n_rows, world_size = int(n_proj), int(n_rows), int(world_size)
+    n_blocks = (n_rows + block - 1) // block
+    total = n_proj * n_blocks
+    out = []
+    for r in range(world_size):
+        lo, hi = shard_bounds(total, world_size, r)
+        runs = []
+        u = lo
+        while u < hi:
+            p = u // n_blocks
+            b_lo = u - p * n_blocks
+            b_hi = min(n_blocks, b_lo + (hi - u))
+            runs.append((p, b_lo * block, min(n_rows, b_hi * block)))
+            u += b_hi - b_lo
+        out.append(runs)
     return out
 
 
-def _small_to(arr, device):
-    """Small host table -> tensor on ``device``; on CUDA through the engine's kernel fetch, so
-    that it does not queue behind a large upload on the copy engine."""
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    if device is None or torch.device(device).type != "cuda":
-        return t if device is None else t.to(device)
-    from . import _engine
-    return _engine.to_device(np.ascontiguousarray(arr), t.dtype)
+def _is_gloo_cuda(t, group=None):
+    return t.is_cuda and dist.get_backend(group) == "gloo"
 
 
-def all_gather_counts(counts, group=None, device=None):
-    """numGenes of every rank's rows, rank-major (host int64 array)."""
-    world_size, rank = world()
-    counts = np.asarray(counts, dtype=np.int64)
+def all_reduce_sum(t, group=None):
+    """In-place sum over the ranks (no-op on one rank)."""
+    world_size, _ = world()
     if world_size == 1:
-        return counts
-    t = _small_to(counts.reshape(1, -1).copy(), device)
-    return all_gather_rows(t, group=group)[0].cpu().numpy()
+        return t
+    if _is_gloo_cuda(t, group):
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
-class GlobalBackground(object):
-    """Index bookkeeping for p-values over the gathered medians.
+def even_bounds(n_rows, world_size):
+    return [shard_bounds(n_rows, world_size, r) for r in range(world_size)]
 
-    Every rank's block is laid out [real rows | random rows]; the gathered
-    matrix is rank-major.  ``real_cols`` / ``rnd_cols`` select the real and the
-    random signatures of all ranks in (rank, row) order -- the order the
-    reference would see had the caller concatenated the per-rank dictionaries.
-    The numGenes grouping is that of Signatures.py:417-439."""
 
-    def __init__(self, counts_all, n_real_per_rank, rows_per_rank, device):
-        from .Signatures import _background_groups
-        counts_all = np.asarray(counts_all, dtype=np.int64)
-        world_size = len(rows_per_rank)
-        real_cols, rnd_cols = [], []
-        off = 0
-        for r in range(world_size):
-            real_cols.extend(range(off, off + n_real_per_rank[r]))
-            rnd_cols.extend(range(off + n_real_per_rank[r], off + rows_per_rank[r]))
-            off += rows_per_rank[r]
-        self.real_cols_host = np.asarray(real_cols, dtype=np.int64)
-        self.rnd_cols_host = np.asarray(rnd_cols, dtype=np.int64)
-        order, gptr, grp = _background_groups(list(counts_all[self.rnd_cols_host]),
-                                              list(counts_all[self.real_cols_host]))
-        self.order_host, self.gptr_host, self.grp_host = order, gptr, grp
-        self.device = device
-        if device is not None and torch.device(device).type == "cuda":
-            self.real_cols = _small_to(self.real_cols_host, device)
-            self.rnd_cols = _small_to(self.rnd_cols_host, device)
-            self.order = _small_to(order, device)
-            self.gptr = _small_to(gptr, device)
-            self.grp = _small_to(grp, device)
+def all_gather_row_blocks(local, bounds, group=None):
+    """local: this rank's block ``bounds[rank] = (lo, hi)`` of a [n_rows x ld] matrix -> the
+    whole matrix on every rank (one all-gather; the blocks are padded to the widest for the
+    collective and compacted afterwards if they are not all equal)."""
+    world_size, rank = world()
+    if world_size == 1:
+        return local
+    ld = local.shape[1]
+    widths = [hi - lo for lo, hi in bounds]
+    widest = max(widths)
+    mine = local
+    if local.shape[0] != widest:
+        mine = torch.zeros((widest, ld), dtype=local.dtype, device=local.device)
+        mine[:local.shape[0]] = local
+    mine = mine.contiguous()
+    buf = torch.empty((world_size * widest, ld), dtype=local.dtype, device=local.device)
+    if _is_gloo_cuda(local, group):
+        hb = torch.empty(buf.shape, dtype=buf.dtype)
+        dist.all_gather_into_tensor(hb, mine.cpu(), group=group)
+        buf.copy_(hb)
+    else:
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    if all(w == widest for w in widths):
+        return buf
+    return torch.cat([buf[r * widest:r * widest + widths[r]] for r in range(world_size)], dim=0)
 
-    def pvalues(self, all_med):
-        """all_med: [P x rows_total] CUDA float64 (gathered) -> [P x K_total]
-        p-values of every rank's real signatures, via fp_background_pvalues."""
-        from . import _engine
-        rows = []
-        for i in range(all_med.shape[0]):
-            med = all_med[i].index_select(0, self.real_cols).contiguous()
-            rnd = all_med[i].index_select(0, self.rnd_cols).contiguous()
-            p, _, _ = _engine.background_pvalues(med, self.grp, rnd, self.order, self.gptr)
-            rows.append(p)
-        return torch.stack(rows)
+
+def broadcast_object(obj, src=0, group=None):
+    world_size, _ = world()
+    if world_size == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]

@@ -65,10 +65,6 @@ extern "C" {
 /* what fp_consistency writes */
 #define FP_OUT_ABS_ERROR       0   /* |r - prediction|  (Signatures.py:408, 413, 462, 470) */
 #define FP_OUT_PREDICTION      1   /* the prediction itself (factor branch, :493, 505)     */
-/* OR-ed into output_kind (FP_PRECISION_TC only): the workspace still holds the packed
- * digit planes of the previous call with the SAME values / N / K (the reference loops
- * over projections with one rank matrix, Signatures.py:393), so packing is skipped */
-#define FP_REUSE_PACKED      0x100
 
 /* arithmetic of the neighbourhood contraction in fp_consistency */
 #define FP_PRECISION_FP64      0   /* float64 FMA on the FP64 pipe (verifier)           */
@@ -198,10 +194,24 @@ int fp_normalize_cols(const double *X, int64_t G, int64_t N, int64_t ld, double 
  *   output_kind  : FP_OUT_*  (the factor branch, :493-508, needs the raw prediction)
  *   precision_mode : FP_PRECISION_*
  *   workspace    : fp_consistency_workspace_bytes(N, K, mode) bytes, 1024-byte aligned
- *                  (0 for FP_PRECISION_FP64); FP_REUSE_PACKED needs the same workspace
- *                  as the previous call
+ *                  (0 for FP_PRECISION_FP64)
+ *
+ * FP_PRECISION_TC represents the values as half-integers of bounded range (average ranks,
+ * one-hot / binary columns).  Anything else (NaN, non-half-integers, a range wider than
+ * three base-256 digits) is refused, not approximated: every output of that call is NaN and a
+ * flag is left in the workspace -- fp_consistency_status() reports it to the host.
  */
 size_t fp_consistency_workspace_bytes(int64_t N, int64_t K, int precision_mode);
+
+/*
+ * fp_consistency_status -- after one or more fp_consistency calls on `workspace` (same
+ * N, K, mode): synchronises `stream` and returns FP_OK, or FP_EUNSUPPORTED if the LAST call
+ * refused its values (see above; fp_last_error() says why).  The reference has no such
+ * state (NumPy float64 takes any value); the Python mirror uses it to raise, or to re-run
+ * the call with FP_PRECISION_FP64, instead of handing NaNs to the caller.
+ */
+int fp_consistency_status(const void *workspace, int64_t N, int64_t K, int precision_mode,
+                          void *stream);
 int fp_consistency(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
                    const double *ranks, int64_t N, int64_t K, int64_t ld,
                    double *out_dissim, int64_t ld_out, int output_kind, int precision_mode,

@@ -1,9 +1,10 @@
-"""world_size-2 gloo tests of the signature-block partitioning (CPU only).
+"""world_size-2/3 gloo tests of the multi-GPU partitioning (CPU only).
 
-The data path of the multi-GPU run has no collective; what is exchanged is the
-[projections x rows] matrix of medians.  These tests run the exchange and the
-index bookkeeping on two gloo ranks and compare the pooled background table
-with the oracle's (Signatures.py:417-439) on the same medians."""
+One job, split two ways (fastproject_b200/distributed.py): rows of the signature batch for
+scoring + ranking, then runs of the (projection x signature-block) grid for the contraction
+and the medians.  The exchanges are one all-gather of row blocks and one all-reduce of the
+[projections x rows] medians.  These tests run both on gloo ranks with a CPU stand-in for the
+per-run kernel and compare with the same job done by one process."""
 import os
 import socket
 
@@ -14,7 +15,6 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from fastproject_b200 import distributed as D
-from oracle import fp_oracle as O
 
 
 def _free_port():
@@ -23,37 +23,6 @@ def _free_port():
     port = s.getsockname()[1]
     s.close()
     return port
-
-
-def _rank_block(rank):
-    """Deterministic per-rank block: [real | random] medians for 2 projections."""
-    rng = np.random.RandomState(100 + rank)
-    n_real = 5 + rank                   # unequal widths on purpose
-    sizes = [5, 10, 20]
-    rnd_counts = np.repeat(sizes, 7 + rank)
-    rng.shuffle(rnd_counts)
-    real_counts = rng.randint(3, 40, size=n_real)
-    counts = np.concatenate([real_counts, rnd_counts]).astype(np.int64)
-    med = rng.normal(loc=300.0, scale=5.0, size=(2, counts.size))
-    return n_real, counts, med
-
-
-def _worker(rank, world_size, port, out_dir):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world_size)
-    try:
-        n_real, counts, med = _rank_block(rank)
-        shape_all = D.all_gather_counts([n_real, counts.size]).reshape(world_size, 2)
-        counts_all = D.all_gather_counts(counts)
-        all_med = D.all_gather_rows(torch.from_numpy(med))
-        bg = D.GlobalBackground(counts_all, [int(v) for v in shape_all[:, 0]],
-                                [int(v) for v in shape_all[:, 1]], device=None)
-        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), shape_all=shape_all,
-                 counts_all=counts_all, all_med=all_med.numpy(), real_cols=bg.real_cols_host,
-                 rnd_cols=bg.rnd_cols_host, order=bg.order_host, gptr=bg.gptr_host, grp=bg.grp_host)
-    finally:
-        dist.destroy_process_group()
 
 
 def test_shard_bounds_cover_and_balance():
@@ -67,32 +36,100 @@ def test_shard_bounds_cover_and_balance():
             assert max(widths) - min(widths) <= 1
 
 
-@pytest.mark.timeout(120)
-def test_two_rank_median_exchange_and_background(tmp_path):
-    world_size = 2
-    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
-    got = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(world_size)]
-    blocks = [_rank_block(r) for r in range(world_size)]
-    want_med = np.concatenate([b[2] for b in blocks], axis=1)
-    want_counts = np.concatenate([b[1] for b in blocks])
-    for g in got:                                   # every rank sees the same, rank-major
-        assert np.array_equal(g["all_med"], want_med)
-        assert np.array_equal(g["counts_all"], want_counts)
-    g = got[0]
-    # the pooled background equals the oracle's table on the concatenated dictionaries
-    real_cols, rnd_cols = g["real_cols"], g["rnd_cols"]
-    assert len(real_cols) == sum(b[0] for b in blocks)
-    for proj in range(want_med.shape[0]):
-        rnd_med = want_med[proj, rnd_cols]
-        rnd_ng = want_counts[rnd_cols]
-        table = O.background_table(rnd_med, rnd_ng)
-        # groups in first-seen order, members in original order
-        for grp in range(table.shape[0]):
-            members = g["order"][g["gptr"][grp]:g["gptr"][grp + 1]]
-            assert np.all(rnd_ng[members] == table[grp, 0])
-            assert np.array_equal(np.sort(members), members)
-            assert np.isclose(np.mean(rnd_med[members]), table[grp, 1], rtol=1e-15)
-        # nearest-numGenes assignment of every real signature (argmin, first wins)
-        for k, col in enumerate(real_cols):
-            want = int(np.argmin(np.abs(want_counts[col] - table[:, 0])))
-            assert g["grp"][k] == want
+@pytest.mark.parametrize("n_proj,n_rows,world", [
+    (6, 3500, 8), (8, 4000, 8), (8, 19000, 8), (4, 3200, 8), (6, 3500, 1), (6, 3500, 2), (6, 3500, 4),
+    (1, 10, 8), (3, 254, 2), (2, 255, 3), (5, 0, 4), (0, 100, 2)])
+def test_partition_units_cover_every_pair_once(n_proj, n_rows, world):
+    runs = D.partition_units(n_proj, n_rows, world)
+    assert len(runs) == world
+    owner = np.zeros((n_proj, n_rows), dtype=np.int64)
+    for r, mine in enumerate(runs):
+        for p, lo, hi in mine:
+            assert 0 <= p < n_proj and 0 <= lo < hi <= n_rows
+            assert lo % D.SIG_BLOCK == 0                       # runs start on a CTA-pair row tile
+            owner[p, lo:hi] += 1
+        # one call of the contraction per projection touched
+        assert len(set(p for p, _, _ in mine)) == len(mine)
+    assert (owner == 1).all()
+    # balance in units of signature blocks
+    n_blocks = (n_rows + D.SIG_BLOCK - 1) // D.SIG_BLOCK
+    units = [sum((hi - lo + D.SIG_BLOCK - 1) // D.SIG_BLOCK for _, lo, hi in mine) for mine in runs]
+    assert sum(units) == n_proj * n_blocks
+    assert max(units) - min(units) <= 1
+
+
+def test_partition_units_is_projection_major_when_projections_divide():
+    # C3: 8 projections on 8 GPUs -> one whole projection per rank (its weight planes are
+    # generated once in the job); on 4 and 2 GPUs whole projections too
+    for world in (8, 4, 2):
+        runs = D.partition_units(8, 4000, world)
+        for r, mine in enumerate(runs):
+            assert [(lo, hi) for _, lo, hi in mine] == [(0, 4000)] * (8 // world)
+    # C2: 6 projections on 8 GPUs -> a rank straddles at most two projections
+    for mine in D.partition_units(6, 3500, 8):
+        assert 1 <= len(mine) <= 2
+
+
+def _job(seed=5, n_rows=37, n_cells=50, n_proj=3):
+    rng = np.random.RandomState(seed)
+    scores = rng.normal(size=(n_rows, n_cells))
+    shifts = rng.normal(size=(n_proj,))
+    return scores, shifts
+
+
+def _stand_in_rank(x):
+    return np.argsort(np.argsort(x, axis=1), axis=1).astype(np.float64) + 1.0
+
+
+def _stand_in_median(ranks_block, shift):
+    return np.median(np.abs(ranks_block - ranks_block.mean(axis=1, keepdims=True) * shift), axis=1)
+
+
+def _worker(rank, world_size, port, out_dir, bounds_kind):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        scores, shifts = _job()
+        n_rows, n_proj = scores.shape[0], shifts.size
+        if bounds_kind == "even":
+            bounds = D.even_bounds(n_rows, world_size)
+        else:                                              # what rejected signatures leave behind
+            cuts = [0, 3, 3 + 20][:world_size] + [n_rows]
+            bounds = [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+        lo, hi = bounds[rank]
+        # stage 1: rank my rows, gather all
+        local = torch.from_numpy(_stand_in_rank(scores[lo:hi]))
+        ranks = D.all_gather_row_blocks(local, bounds)
+        # stage 2: my runs of the (projection x block) grid (tiny blocks so that runs straddle)
+        med = torch.zeros((n_proj, n_rows), dtype=torch.float64)
+        for p, rlo, rhi in D.partition_units(n_proj, n_rows, world_size, block=5)[rank]:
+            med[p, rlo:rhi] = torch.from_numpy(_stand_in_median(ranks[rlo:rhi].numpy(), shifts[p]))
+        D.all_reduce_sum(med)
+        got = D.broadcast_object({"from": rank} if rank == 0 else None)
+        assert got == {"from": 0}
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ranks=ranks.numpy(), med=med.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world_size,bounds_kind", [(2, "even"), (3, "ragged")])
+def test_gloo_ranks_reproduce_the_single_process_job(tmp_path, world_size, bounds_kind):
+    mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path), bounds_kind), nprocs=world_size,
+             join=True)
+    scores, shifts = _job()
+    want_ranks = _stand_in_rank(scores)
+    want_med = np.stack([_stand_in_median(want_ranks, s) for s in shifts])
+    for r in range(world_size):                    # every rank ends with the whole result, bit for bit
+        got = np.load(str(tmp_path / ("rank%d.npz" % r)))
+        assert np.array_equal(got["ranks"], want_ranks)
+        assert np.array_equal(got["med"], want_med)
+
+
+def test_single_process_helpers_are_identity():
+    t = torch.arange(12, dtype=torch.float64).reshape(3, 4)
+    assert D.world() == (1, 0)
+    assert D.all_gather_row_blocks(t, [(0, 3)]) is t
+    assert D.all_reduce_sum(t) is t
+    assert D.broadcast_object("x") == "x"
