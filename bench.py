@@ -2,33 +2,38 @@
 # -*- coding: utf-8 -*-
 """Benchmark of the FastProject scoring core on B200 ("Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C3|C4]
 
-A *step* is one pass of the hot path over one batch of synthetic input of the
-shape BASELINE.json's metric is quoted on (configs[1]: 20k cells x 15k genes,
-500 signatures + 3000 random signatures, 6 projections):
+A *step* is one pass of the hot path over ONE job of synthetic input:
 
-    score all signatures  ->  rank  ->  per projection: fused Gaussian-
-    neighbourhood contraction, median, background p-values.
+    score all signatures  ->  rank  ->  per projection: Gaussian-neighbourhood contraction,
+    median over the cells, background p-values.
 
-Metric: signature x projection consistency pairs / s = (K+R)*P / t_step (whole
-job).  ``value`` is timed with CUDA events with every input resident in HBM;
-``e2e`` times the public Python mirror of the reference API with HOST (pinned)
-inputs, host<->device copies inside the timed region.  The cell x signature
-scores / s half of the metric is reported beside it (``scores_per_sec``).
+The headline workload is BASELINE.json configs[1] (C2: 20k cells x 15k genes, 500 signatures +
+3000 random signatures, 6 projections); the line also carries a ``"c3"`` block -- the north-star
+shape (100k cells x 20k genes, 1000 + 3000 signatures, 8 projections) run the same way with
+fewer steps.
 
-N > 1 (torchrun): the signature blocks (real + random) are sharded over the
-ranks, every rank holds the full expression matrix and all projections, and
-the only exchange is an all-gather of the per-signature medians (weak scaling:
-per-GPU work is fixed, the job has N x the signatures).
+Metric: signature x projection consistency pairs / s = (K + R) * P / t_step for the whole job.
+``value`` is timed with CUDA events with every input resident in HBM; ``e2e`` times the public
+Python mirror of the reference API with HOST (pinned) inputs, host<->device copies inside the
+timed region.  The cell x signature scores / s half of the metric is ``scores_per_sec``.
 
-``--impl reference`` times the CPU restatement of the reference (the oracle
-port; the reference is pure Python/NumPy and cannot travel to the GPU box) on a
-bounded row-sample of the same workload, on the host cores of the box.
+N > 1 (torchrun, one process per GPU): the SAME job is split over the ranks ("scaling":
+"strong") -- scoring and ranking by signature rows, the contraction by runs of the (projection
+x signature-block) grid, with one all-gather of the rank rows and one all-reduce of the medians
+(fastproject_b200/distributed.py).
+
+CPU legs.  ``cpu_baseline`` (rank 0, N = 1): ONE WHOLE job of the same inputs on the host cores
+-- the unmodified reference from baseline/_ref (kind "reference") when it is installed, else
+the restatement in oracle/fp_oracle.py (kind "port") -- timed as a whole, not scaled from a
+sample; its outputs are the checker of ``parity``.  ``--impl reference`` deals the units of one
+whole job to the K timed steps (a step is 1/K of the job; the steps together are the job).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -48,72 +53,90 @@ WORKLOADS = {
 }
 SIZES = [5, 10, 20, 50, 100, 200]
 SIGMA = 0.33
+SEED = 1335607828
+METRIC = ("signature x projection consistency pairs/sec (full hot path: score + rank + "
+          "consistency + median + p-values)")
 
 
 def describe_config(workload, cfg, n_real, n_rnd, precision, world):
     """The ``config`` object of the JSON line -- identical for both arms."""
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
-    return {"workload": "%s: %d cells x %d genes, %d real + %d random signatures per GPU, "
-                        "%d projections, sigma=0.33" % (workload, N, G, n_real, n_rnd, P),
-            "precision_mode": precision, "signatures_per_gpu": n_real + n_rnd,
+    return {"workload": "%s: %d cells x %d genes, %d real + %d random signatures, %d projections, "
+                        "sigma=0.33; one job for all GPUs" % (workload, N, G, n_real, n_rnd, P),
+            "precision_mode": precision, "signatures": n_real + n_rnd,
             "l2_policy": "inputs larger than L2 (X+W = %.1f GB per step)" % (G * N * 16 / 1e9),
-            "parallelism": "signature-block x%d" % world}
+            "parallelism": "1 GPU" if world == 1 else
+                           "%d GPUs: signature rows for scoring/ranking, (projection x signature-block) "
+                           "runs for the contraction" % world}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FP_BENCH_WORKLOAD", "C2"))
     ap.add_argument("--precision", default=None, help="fp64 | tc (default: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 block")
+    ap.add_argument("--c3-steps", type=int, default=3)
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------
 # synthetic workload
 # ----------------------------------------------------------------------------
-def make_workload(cfg, device, seed=1335607828, sig_seed=None):
-    """Synthetic inputs of SURVEY.md 8d's recipe, generated on the device for
-    speed (log1p-Gamma counts with ~40 % zeros, per-gene z-score, detection
-    weights), signatures on the host with the reference's RNG calls."""
+def make_signatures(cfg, genes, seed=SEED):
+    import random
+    import numpy as np
+    from fastproject_b200 import Signatures as S, synth
+    defs = synth.make_signature_dicts(genes, cfg["K"], seed=seed + 2)
+    real = [S.Signature(d, sg, "synthetic", nm) for nm, d, sg in defs]
+    random.seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    rnd = S.generate_random_sigs(genes, False, SIZES, cfg["R_PER_SIZE"])
+    return real, rnd
+
+
+def make_workload(cfg, device, seed=SEED, keep_raw=False):
+    """Synthetic inputs of SURVEY.md 8d's recipe, generated on the device for speed: raw
+    log1p-Gamma counts with ~40 % zeros; per-cell logistic false-negative curves; then the two
+    matrices the path reads, made the way the pipeline makes them (Pipelines.py:114-120, 202):
+    W = compute_weights(raw, curves), X = per-gene z-score of raw.  Signatures on the host with
+    the reference's RNG calls.  Every rank builds the same job."""
     import numpy as np
     import torch
-    from fastproject_b200 import Signatures as S, synth
+    from fastproject_b200 import _engine as E, synth
     G, N = cfg["G"], cfg["N"]
     gen = torch.Generator(device=device)
     gen.manual_seed(seed % (2 ** 31))
-    x = torch.empty((G, N), dtype=torch.float64, device=device)
-    w = torch.empty((G, N), dtype=torch.float64, device=device)
+    projections, gradient = synth.make_projections(N, cfg["P"], seed=seed + 1)
+    # a gradient along the first projection planted into the first 150 genes (the first five
+    # real signatures draw from them): some signature x projection pairs are genuinely
+    # consistent, so the significance calls of the parity check are not all "no"
+    planted = torch.from_numpy(np.maximum(gradient, 0.0)).to(device)
+    raw = torch.empty((G, N), dtype=torch.float64, device=device)
     chunk = 1024
     for lo in range(0, G, chunk):
         hi = min(G, lo + chunk)
         shape = (hi - lo, N)
         # Gamma(shape .5, scale 4) = 4 * 0.5 * chi2_1 = 2 * z^2
-        raw = torch.log1p(2.0 * torch.randn(shape, generator=gen, device=device, dtype=torch.float64) ** 2)
-        raw = raw * (torch.rand(shape, generator=gen, device=device) < 0.6)
-        u = torch.rand(shape, generator=gen, device=device, dtype=torch.float64)
-        w[lo:hi] = torch.where(raw > 0, torch.ones_like(raw), u)
-        mu = raw.mean(dim=1, keepdim=True)
-        sd = raw.std(dim=1, keepdim=True, unbiased=False)
-        sd[sd == 0] = 1.0
-        x[lo:hi] = (raw - mu) / sd
+        r = torch.log1p(2.0 * torch.randn(shape, generator=gen, device=device, dtype=torch.float64) ** 2)
+        if lo < 150:
+            k = min(hi, 150) - lo
+            r[:k] += planted[None, :] * (0.5 + torch.rand((k, 1), generator=gen, device=device, dtype=torch.float64))
+        raw[lo:hi] = r * (torch.rand(shape, generator=gen, device=device) < 0.6)
+    rng = np.random.RandomState(seed % (2 ** 31))
+    params = np.stack([rng.uniform(0.5, 2.5, N), rng.uniform(0.5, 3.0, N), np.zeros(N), np.ones(N)])
+    w = E.compute_weights(raw, E.to_device(params))
+    x = E.normalize_rows(raw)
     genes = ["G%05d" % i for i in range(G)]
     cells = ["C%06d" % i for i in range(N)]
-    projections, _ = synth.make_projections(N, cfg["P"], seed=seed + 1)
-    # one data set (expression, weights, projections) for the whole job; every rank owns its
-    # own block of real + random signatures
-    sig_seed = seed if sig_seed is None else sig_seed
-    defs = synth.make_signature_dicts(genes, cfg["K"], seed=sig_seed + 2)
-    real = [S.Signature(d, sg, "synthetic", nm) for nm, d, sg in defs]
-    import random
-    random.seed(sig_seed)
-    np.random.seed(sig_seed % (2 ** 32))
-    rnd = S.generate_random_sigs(genes, False, SIZES, cfg["R_PER_SIZE"])
-    return dict(x=x, w=w, genes=genes, cells=cells, projections=projections, real=real, rnd=rnd)
+    real, rnd = make_signatures(cfg, genes, seed)
+    return dict(x=x, w=w, raw=raw if keep_raw else None, params=params, genes=genes, cells=cells,
+                projections=projections, real=real, rnd=rnd)
 
 
 # ----------------------------------------------------------------------------
@@ -174,7 +197,7 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------
-# B200 arm
+# B200 arm: the job with every input resident in HBM
 # ----------------------------------------------------------------------------
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -184,6 +207,279 @@ def measured_peaks():
         return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), tflops=d.get("bf16_tflops_sustained", 1400.0),
                     source="measured (MEASURED_PEAKS.json, sustained bf16)")
     return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def captured_traffic(workload, precision, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the committed
+    ``ncu --set full`` capture of this workload (profiles/r02_traffic.json names the capture file
+    and its sha256); None when no capture of this configuration is committed."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as fh:
+        table = json.load(fh)
+    entry = table.get("%s/%s/%s" % (workload, precision, kernel))
+    if not entry:
+        return None, None
+    return entry.get("dram_bytes_per_launch"), entry.get("source")
+
+
+class ResidentJob(object):
+    """One job on this rank's share of the work; inputs resident in HBM."""
+
+    def __init__(self, name, cfg, wl, device, world, rank, precision):
+        import numpy as np
+        import torch
+        from fastproject_b200 import Signatures as S, _engine as E, _scoring, distributed as D
+        self.name, self.cfg, self.wl, self.device, self.world, self.rank = name, cfg, wl, device, world, rank
+        self.E, self.D, self.S, self.torch = E, D, S, torch
+        self.precision = precision
+        G, N, P = cfg["G"], cfg["N"], cfg["P"]
+        sigs = wl["real"] + wl["rnd"]
+        kept, sig_ptr, sig_gene, sig_sign, counts = _scoring.pack_signatures(sigs, wl["genes"], 5)
+        self.n_real = sum(1 for k in kept if k < len(wl["real"]))
+        self.n_rows = len(kept)
+        self.counts = counts
+        self.nnz = int(sig_ptr[-1])
+        # stage 1: my rows of the signature batch
+        self.bounds = D.even_bounds(self.n_rows, world)
+        lo, hi = self.bounds[rank]
+        self.rows = (lo, hi)
+        e0, e1 = int(sig_ptr[lo]), int(sig_ptr[hi])
+        self.nnz_local = e1 - e0
+        self.d_ptr = E.to_device((sig_ptr[lo:hi + 1] - sig_ptr[lo]).astype(np.int32), torch.int32)
+        self.d_gene = E.to_device(sig_gene[e0:e1], torch.int32)
+        self.d_sign = E.to_device(sig_sign[e0:e1], torch.int8)
+        # stage 2: my runs of the (projection x signature-block) grid
+        self.proj_names = sorted(wl["projections"].keys())
+        self.coords = E.to_device(np.stack([wl["projections"][p] for p in self.proj_names]))
+        if world > 1:
+            self.runs = D.partition_units(P, self.n_rows, world)[rank]
+        else:
+            self.runs = [(p, 0, self.n_rows) for p in range(P)]
+        order, gptr, grp = S._background_groups(list(counts[self.n_real:]), list(counts[:self.n_real]))
+        self.d_order = E.to_device(order, torch.int32)
+        self.d_gptr = E.to_device(gptr, torch.int32)
+        self.d_grp = E.to_device(grp, torch.int32)
+        self.ld = E.padded(N)
+        widest = max([h - l for _, l, h in self.runs] or [1])
+        self.dissim = torch.empty((widest, self.ld), dtype=torch.float64, device=device)
+        self.med_all = torch.zeros((P, self.n_rows), dtype=torch.float64, device=device)
+        self.p_all = torch.empty((P, self.n_real), dtype=torch.float64, device=device)
+        self.sig2 = SIGMA ** 2
+        self.events = []              # (stage, start, stop) of the recorded steps
+
+    def _ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def step(self, record=False):
+        E, D, torch = self.E, self.D, self.torch
+        N, P = self.cfg["N"], self.cfg["P"]
+        marks = []
+
+        def mark(stage):
+            if record:
+                e = self._ev()
+                e.record()
+                marks.append((stage, e))
+
+        mark("begin")
+        scores = E.score_signatures("weighted_avg", self.wl["x"], self.wl["w"], None, self.d_ptr, self.d_gene,
+                                    self.d_sign, self.rows[1] - self.rows[0])
+        mark("score")
+        ranks = E.rank_rows(scores, N)
+        mark("rank")
+        if self.world > 1:
+            ranks = D.all_gather_row_blocks(ranks, self.bounds)
+            self.med_all.zero_()
+        mark("gather")
+        for p, lo, hi in self.runs:
+            dis = E.consistency(self.coords[p], self.sig2, ranks[lo:hi], N, out=self.dissim[:hi - lo],
+                                precision=self.precision, slot="bench")
+            mark("consistency")
+            self.med_all[p, lo:hi] = E.row_medians(dis, N)
+            mark("median")
+        if self.world > 1:
+            D.all_reduce_sum(self.med_all)
+        for i in range(P):
+            p, _, _ = E.background_pvalues(self.med_all[i, :self.n_real].contiguous(), self.d_grp,
+                                           self.med_all[i, self.n_real:].contiguous(), self.d_order, self.d_gptr)
+            self.p_all[i] = p
+        mark("reduce+pvalues")
+        if record:
+            self.events.append(marks)
+        self.last_scores, self.last_ranks = scores, ranks
+        return self.p_all, self.med_all
+
+    def stage_ms(self):
+        """Mean milliseconds per step of every stage, from the recorded events (this rank)."""
+        out = dict()
+        for marks in self.events:
+            for (_, a), (stage, b) in zip(marks[:-1], marks[1:]):
+                out[stage] = out.get(stage, 0.0) + a.elapsed_time(b)
+        n = max(1, len(self.events))
+        return dict((k, v / n) for k, v in out.items())
+
+    def results(self):
+        """Host copies in the reference's layout: consistency [K x P], log10 q [K x P],
+        background consistency [R x P]."""
+        import numpy as np
+        N = self.cfg["N"]
+        med = self.med_all.cpu().numpy()
+        cons = 1 - med[:, :self.n_real].T / N
+        rnd_cons = 1 - med[:, self.n_real:].T / N
+        q = self.S.p_to_q(self.p_all.cpu().numpy().T.copy())
+        q[q == 0] = 1e-300
+        with np.errstate(invalid="ignore", divide="ignore"):
+            logq = np.log10(q)
+        return cons, logq, rnd_cons
+
+
+def timed_run(job, steps, warmup, world, sampler=None):
+    """W warm-up steps, then exactly K steps between barrier + synchronize; CUDA events, max over
+    ranks.  Returns (ms per step, launches in the timed region, clocks)."""
+    import torch
+    import torch.distributed as dist
+    from fastproject_b200 import _native
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        job.step(False)
+    sync()
+    if sampler is not None:
+        sampler.start()
+    launches0 = _native.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t0.record()
+    for _ in range(steps):
+        job.step(True)
+    t1.record()
+    sync()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=job.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if job.runs:
+        _, lo, hi = job.runs[-1]
+        if job.E.consistency_refused(job.last_ranks[lo:hi], job.cfg["N"], precision=job.precision, slot="bench"):
+            raise RuntimeError("the tensor-core path refused the rank values: the timed results are NaN")
+    return float(t[0]) / steps, int(launches), clocks
+
+
+def rooflines(job, ms_step, workload):
+    """roofline of the dominant kernel (the contraction: tensor pipe) and of the scoring kernel
+    (HBM), from this rank's stage times."""
+    cfg = job.cfg
+    G, N = cfg["G"], cfg["N"]
+    peaks = measured_peaks()
+    st = job.stage_ms()
+    run_rows = sum(hi - lo + 1 for _, lo, hi in job.runs)            # + the ones row of every launch
+    cons_ms = st.get("consistency", 0.0)                              # all of this rank's launches, per step
+    n_launch = max(1, len(job.runs))
+    cons_flops = 2.0 * N * N * run_rows
+    traffic, traffic_src = captured_traffic(workload, job.precision, "fp_consistency")
+    roof = dict(bound="tensor", kernel="fp_consistency[%s]" % job.precision,
+                achieved=cons_flops / max(cons_ms, 1e-9) / 1e9, peak=peaks["tflops"], unit="TFLOP/s",
+                traffic=traffic, traffic_source=traffic_src, peak_source=peaks["source"],
+                launch_ms=cons_ms / n_launch, launches_per_step=n_launch,
+                share_of_step=cons_ms / ms_step,
+                algorithmic="2*N^2 flop per (signature, projection) pair; one launch = one projection x "
+                            "(this rank's rows + 1 normaliser row)")
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    rows_local = job.rows[1] - job.rows[0]
+    score_ms = st.get("score", 0.0)
+    score_bytes = G * N * 16.0 + N * rows_local * 8.0 + 5.0 * job.nnz_local
+    s_traffic, s_src = captured_traffic(workload, job.precision, "fp_score_signatures")
+    roof_s = dict(bound="hbm", kernel="fp_score_signatures", unit="GB/s",
+                  achieved=score_bytes / max(score_ms, 1e-9) / 1e6, peak=peaks["hbm_gbs"],
+                  launch_ms=score_ms, traffic=s_traffic, traffic_source=s_src,
+                  gather_bytes=16.0 * job.nnz_local * N, share_of_step=score_ms / ms_step,
+                  algorithmic="X and W once (16 B per gene x cell) + 8 B per score + 5 B per signature gene")
+    roof_s["frac"] = roof_s["achieved"] / roof_s["peak"]
+    return roof, roof_s, st
+
+
+def compare_with_cpu(job, cpu):
+    """``parity`` of the timed workload: the GPU job's outputs against the whole CPU job's."""
+    import numpy as np
+    cons, logq, rnd_cons = job.results()
+    scores = job.E.to_host(job.last_scores[:, :job.cfg["N"]])            # N = 1: all rows
+    ref_scores = np.concatenate([cpu.scores_matrix("real"), cpu.scores_matrix("rnd")], axis=0)
+    out = {"checker": "whole job on the host: " + cpu.kind, "cells_checked": job.cfg["N"],
+           "signatures_checked": int(ref_scores.shape[0]), "projections_checked": len(job.proj_names),
+           "scores_bit_identical": bool(scores.shape == ref_scores.shape and np.array_equal(scores, ref_scores))}
+    rel = np.abs(cons - cpu.cons) / np.abs(cpu.cons)
+    rel_r = np.abs(rnd_cons - cpu.rnd_cons) / np.abs(cpu.rnd_cons)
+    out["max_rel_err"] = float(max(rel.max(), rel_r.max()))
+    out["tolerance"] = 1e-6
+    both = np.isfinite(logq) & np.isfinite(cpu.logq)
+    out["max_abs_err_log10q"] = float(np.abs(logq[both] - cpu.logq[both]).max()) if both.any() else None
+    out["ranking_identical"] = bool(np.array_equal(np.argsort(logq, axis=None, kind="stable"),
+                                                   np.argsort(cpu.logq, axis=None, kind="stable")))
+    out["significance_calls_identical"] = bool(np.array_equal(logq < -1.3, cpu.logq < -1.3))
+    out["significant_pairs"] = int((cpu.logq < -1.3).sum())
+    out["ok"] = bool(out["scores_bit_identical"] and out["max_rel_err"] <= 1e-6 and out["ranking_identical"]
+                     and out["significance_calls_identical"])
+    return out
+
+
+def subset_parity(job, n_sigs=16, n_cells=1024):
+    """Parity on a SUBSET for shapes whose whole job the host cannot do in minutes (C3; and any
+    N > 1 run): the first signatures of this rank's first run are scored and ranked by the oracle
+    from the gene rows they use (bit-exact comparison), and ``n_cells`` rows of the N x N kernel
+    of that projection are contracted by the row-blocked oracle and compared with the GPU's
+    |rank - prediction| for those cells."""
+    import numpy as np
+    import torch
+    from oracle import fp_oracle as O
+    if not job.runs or job.rank != 0:
+        return None
+    p, lo, hi = job.runs[0]
+    N = job.cfg["N"]
+    take = min(n_sigs, hi - lo, job.rows[1] - job.rows[0])
+    sigs = (job.wl["real"] + job.wl["rnd"])
+    from fastproject_b200 import _scoring
+    kept, _, _, _, _ = _scoring.pack_signatures(sigs, job.wl["genes"], 5)
+    chosen = [sigs[kept[r]] for r in range(lo, lo + take)]
+    gene_pos = dict((g, i) for i, g in enumerate(job.wl["genes"]))
+    rows = sorted(set(gene_pos[g] for s in chosen for g in s.sig_dict if g in gene_pos))
+    idx = torch.tensor(rows, dtype=torch.long, device=job.device)
+    xs = job.wl["x"].index_select(0, idx).cpu().numpy()
+    ws = job.wl["w"].index_select(0, idx).cpu().numpy()
+    odata = O.ExpressionMatrix(xs, ws, [job.wl["genes"][r] for r in rows], job.wl["cells"])
+    ores = O.calculate_sig_scores(odata, [O.Signature(s.sig_dict, s.signed, s.source, s.name) for s in chosen],
+                                  "weighted_avg", None, 5)
+    want_scores = np.array([ores[s.name].scores for s in chosen])
+    want_ranks = np.array([ores[s.name].ranks for s in chosen])
+    # GPU: scores / ranks of those rows (rank 0's rows start at 0 = lo) and the contraction
+    got_scores = job.last_scores[:take, :N].cpu().numpy()
+    got_ranks = job.last_ranks[lo:lo + take, :N].cpu().numpy()
+    dis = job.E.consistency(job.coords[p], job.sig2, job.last_ranks[lo:hi], N, out=job.dissim[:hi - lo],
+                            precision=job.precision, slot="bench")
+    cells = np.sort(np.random.RandomState(11).choice(N, size=min(n_cells, N), replace=False))
+    got = dis[:take].index_select(1, torch.from_numpy(cells).to(job.device)).cpu().numpy()
+    coords = job.wl["projections"][job.proj_names[p]]
+    want = np.empty_like(got)
+    vt = np.ascontiguousarray(want_ranks.T)
+    for b in range(0, cells.size, 256):
+        sel = cells[b:b + 256]
+        wt = O.neighbourhood_weights(coords, SIGMA, sel)
+        want[:, b:b + 256] = np.abs(vt[sel] - np.dot(wt, vt)).T
+    err = float(np.abs(got - want).max())
+    return {"checker": "oracle port on a subset (scores and ranks from the gene rows used; row-blocked "
+                       "N x N kernel)", "signatures_checked": int(take), "cells_checked": int(cells.size),
+            "projection": job.proj_names[p],
+            "scores_bit_identical": bool(np.array_equal(got_scores, want_scores)),
+            "ranks_bit_identical": bool(np.array_equal(got_ranks, want_ranks)),
+            "max_abs_err_rank_units": err, "max_rel_err": err / N, "tolerance": 1e-6,
+            "ok": bool(np.array_equal(got_scores, want_scores) and np.array_equal(got_ranks, want_ranks)
+                       and err / N <= 1e-6)}
 
 
 def run_b200(args):
@@ -198,133 +494,51 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout at VERSION/INFO level; stdout carries the JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("FP_NCCL_DEBUG", "WARN")
+        # NCCL_DEBUG is the caller's: whatever NCCL prints goes to stderr (fd 1 is the JSON line's)
         dist.init_process_group("nccl", device_id=device)
     if rank == 0:
         ge.build()
     if world > 1:
         dist.barrier()
-    from fastproject_b200 import Signatures as S, _engine as E, _native, _scoring, synth, distributed as D
+    from fastproject_b200 import _engine as E
 
     cfg = WORKLOADS[args.workload]
     precision = E.resolve_precision(args.precision, cfg["N"])
-    # weak scaling: every rank owns its own block of K real + R random signatures
-    wl = make_workload(cfg, device, seed=1335607828, sig_seed=1335607828 + 7919 * rank)
-    G, N, P = cfg["G"], cfg["N"], cfg["P"]
-    x, w = wl["x"], wl["w"]
-    sigs = wl["real"] + wl["rnd"]
-    kept, sig_ptr, sig_gene, sig_sign, counts = _scoring.pack_signatures(sigs, wl["genes"], 5)
-    n_real = sum(1 for k in kept if k < len(wl["real"]))
-    n_rows = len(kept)
-    nnz = int(sig_ptr[-1])
-    d_ptr = E.to_device(sig_ptr, torch.int32)
-    d_gene = E.to_device(sig_gene, torch.int32)
-    d_sign = E.to_device(sig_sign, torch.int8)
-    proj_names = sorted(wl["projections"].keys())
-    coords = [E.to_device(wl["projections"][p]) for p in proj_names]
-    # who owns what: [n_real, n_rows] of every rank, and every row's numGenes
-    shape_all = D.all_gather_counts([n_real, n_rows], device=device).reshape(world, 2)
-    counts_all = D.all_gather_counts(counts, device=device)
-    bg = D.GlobalBackground(counts_all, [int(v) for v in shape_all[:, 0]],
-                            [int(v) for v in shape_all[:, 1]], device)
-    ld = E.padded(N)
-    dissim = torch.empty((n_rows, ld), dtype=torch.float64, device=device)
-    sig2 = SIGMA ** 2
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    score_ev, cons_ev = [], []
-
-    def step(record):
-        e0, e1 = ev(), ev()
-        e0.record()
-        scores = E.score_signatures("weighted_avg", x, w, None, d_ptr, d_gene, d_sign, n_rows)
-        e1.record()
-        if record:
-            score_ev.append((e0, e1))
-        ranks = E.rank_rows(scores, N)
-        meds = []
-        for ic, c in enumerate(coords):
-            c0, c1 = ev(), ev()
-            c0.record()
-            E.consistency(c, sig2, ranks, N, out=dissim, precision=precision, reuse_packed=ic > 0,
-                          slot="bench")
-            c1.record()
-            if record:
-                cons_ev.append((c0, c1))
-            meds.append(E.row_medians(dissim, N))
-        med = torch.stack(meds)                               # [P x rows]
-        all_med = D.all_gather_rows(med)                      # the only exchange: P x rows doubles
-        return bg.pvalues(all_med), all_med
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(False)
-    sync()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = _native.launch_count()
-    t0, t1 = ev(), ev()
-    sync()
-    t0.record()
-    for _ in range(args.steps):
-        out = step(True)
-    t1.record()
-    sync()
-    launches = _native.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = t0.elapsed_time(t1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t[0]) / args.steps
-    score_ms = sum(a.elapsed_time(b) for a, b in score_ev) / max(1, len(score_ev))
-    cons_ms = sum(a.elapsed_time(b) for a, b in cons_ev) / max(1, len(cons_ev))
-
-    pairs = int(shape_all[:, 1].sum()) * P
-    value = pairs / (ms_step * 1e-3)
-    peaks = measured_peaks()
-    cons_flops = 2.0 * N * N * (n_rows + 1)                   # per launch (one projection)
-    score_bytes = G * N * 16.0 + N * n_rows * 8.0 + 5.0 * nnz  # per launch
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of
-    # this exact configuration (profiles/r01_summary_slab.md); None where no capture exists
-    # (tc: weight_planes_kernel 0.0043 + 1.5572 GB and consistency_mma_kernel 12.4369 + 0.6883 GB)
-    ncu_traffic = {("C2", "tc", 1): 4314000 + 1557239000 + 12436882000 + 688290000,
-                   ("C2", "fp64", 1): 603465984 + 551192064}
-    roofline = dict(bound="tensor", kernel="fp_consistency[%s]" % precision,
-                    achieved=cons_flops / (cons_ms * 1e-3) / 1e12, peak=peaks["tflops"],
-                    unit="TFLOP/s", traffic=ncu_traffic.get((args.workload, precision, 1)),
-                    peak_source=peaks["source"],
-                    launch_ms=cons_ms, share_of_step=cons_ms * P / ms_step)
-    roofline["frac"] = roofline["achieved"] / roofline["peak"]
-    roofline_score = dict(bound="hbm", kernel="fp_score_signatures", unit="GB/s",
-                          achieved=score_bytes / (score_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
-                          launch_ms=score_ms, traffic=None,
-                          gather_bytes=16.0 * nnz * N, share_of_step=score_ms / ms_step)
-    roofline_score["frac"] = roofline_score["achieved"] / roofline_score["peak"]
-
+    want_e2e = not args.no_e2e
+    wl = make_workload(cfg, device, keep_raw=want_e2e)
+    job = ResidentJob(args.workload, cfg, wl, device, world, rank, precision)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, launches, clocks = timed_run(job, args.steps, args.warmup, world, sampler)
+    P = cfg["P"]
+    roof, roof_s, stages = rooflines(job, ms_step, args.workload)
     result = {
-        "metric": "signature x projection consistency pairs/sec (full hot path: score + rank + "
-                  "consistency + median + p-values)",
-        "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if precision == "fp64" else "f64 + u8*s8->s32 digit planes (tcgen05 kind::i8)",
+        "metric": METRIC, "value": job.n_rows * P / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if precision == "fp64" else "f64 + u8*s8->s32 digit planes (tcgen05 kind::i8)",
         "data": "synthetic",
-        "config": describe_config(args.workload, cfg, n_real, n_rows - n_real, precision, world),
-        "scores_per_sec": N * n_rows * world / (score_ms * 1e-3),
-        "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_scoring": roofline_score,
-        "clocks": clocks,
+        "config": describe_config(args.workload, cfg, job.n_real, job.n_rows - job.n_real, precision, world),
+        "scores_per_sec": cfg["N"] * job.n_rows / (max(stages.get("score", 0.0), 1e-9) * 1e-3),
+        "gpu_launches": launches, "roofline": roof, "roofline_scoring": roof_s,
+        "stage_ms_rank0": stages, "clocks": clocks,
     }
+    out = job.step(False)
     result["checksum_p"] = float(out[0].sum())
     result["checksum_median"] = float(out[1].sum())
 
-    if not args.no_e2e:
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"], cpu = cpu_whole_job(cfg, wl)
+        result["parity"] = compare_with_cpu(job, cpu)
+        del cpu
+    elif not args.no_cpu_baseline:
+        par = subset_parity(job)
+        if rank == 0:
+            result["parity"] = par
+    if world > 1:
+        dist.barrier()
+
+    if want_e2e:
         try:
             e2e = run_e2e(args, cfg, wl, precision, world, device)
         except torch.OutOfMemoryError as exc:          # e.g. C4: the device leg's buffers + two data sets
@@ -333,8 +547,17 @@ def run_b200(args):
             e2e = {"unavailable": "out of device memory in the end-to-end leg: %s" % str(exc).split(".")[0]}
         if rank == 0:
             result["e2e"] = e2e
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(cfg, wl, budget_s=25.0)
+
+    # the north-star shape, same arm, fewer steps
+    if not args.no_c3 and args.workload == "C2":
+        del job
+        for k in ("x", "w", "raw"):
+            wl[k] = None
+        E.clear_device_cache()
+        torch.cuda.empty_cache()
+        c3 = run_block("C3", args, device, world, rank, args.c3_steps, 1)
+        if rank == 0:
+            result["c3"] = c3
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -342,194 +565,277 @@ def run_b200(args):
         emit(result)
 
 
+def run_block(name, args, device, world, rank, steps, warmup):
+    """Another workload through the same resident arm; returns a JSON-ready block."""
+    import torch.distributed as dist
+    from fastproject_b200 import _engine as E
+    cfg = WORKLOADS[name]
+    precision = E.resolve_precision(args.precision, cfg["N"])
+    wl = make_workload(cfg, device)
+    job = ResidentJob(name, cfg, wl, device, world, rank, precision)
+    ms_step, launches, _ = timed_run(job, steps, warmup, world, None)
+    roof, roof_s, stages = rooflines(job, ms_step, name)
+    block = {"value": job.n_rows * cfg["P"] / (ms_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
+             "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "scaling": "strong",
+             "config": describe_config(name, cfg, job.n_real, job.n_rows - job.n_real, precision, world),
+             "scores_per_sec": cfg["N"] * job.n_rows / (max(stages.get("score", 0.0), 1e-9) * 1e-3),
+             "gpu_launches": launches, "roofline": roof, "roofline_scoring": roof_s, "stage_ms_rank0": stages}
+    if not args.no_cpu_baseline:
+        par = subset_parity(job)
+        if rank == 0:
+            block["parity"] = par
+            if world == 1:
+                block["cpu_baseline"] = cpu_sampled(cfg, wl, budget_s=20.0)
+    if world > 1:
+        dist.barrier()
+    return block
+
+
 def run_e2e(args, cfg, wl, precision, world=1, device=None):
-    """Public API with HOST buffers: H2D of X and W from pinned memory, CSR
-    packing, all kernels, D2H of the real signatures' scores and of the
-    result matrices, every step.  With N ranks every rank runs the same calls on
-    its own block of signatures (``distributed=True``: medians all-gathered inside
-    ``sigs_vs_projections``); the time is the max over ranks."""
-    import io
-    import contextlib
+    """Public API with HOST buffers, the pipeline's own order (Pipelines.py:114-120, 202-253):
+    H2D of the raw expression matrix from pinned memory, false-negative weights and per-gene
+    z-scores on the device (Transforms.compute_weights / NormalizationMethods.row_normalization
+    mirrors), signature matching + CSR packing on the host, scoring, ranks, all projections,
+    D2H of the real signatures' scores and of the result matrices -- every step.  With N ranks
+    every rank makes the same calls (``distributed=True``): ONE job, the time is the max over
+    ranks."""
     import torch
     import torch.distributed as dist
-    from fastproject_b200 import Signatures as S, _engine as E, synth
-    G, N, P = cfg["G"], cfg["N"], cfg["P"]
     import fastproject_b200 as FP
-    # two sets of pinned host buffers: consecutive steps are different host arrays, so every
-    # step uploads its own inputs; the upload of step k+1 is started at the beginning of step k
-    # (fastproject_b200.prefetch) and runs behind the whole step
+    from fastproject_b200 import Signatures as S, Transforms as T, NormalizationMethods as NM, _engine as E, synth
+    G, N, P = cfg["G"], cfg["N"], cfg["P"]
+    # two pinned host buffers: consecutive steps are different host arrays, so every step uploads
+    # its own input; the upload of step k+1 is started at the beginning of step k
     host = []
     for _ in range(2):
-        xh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
-        wh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
-        xh.copy_(wl["x"]); wh.copy_(wl["w"])
-        host.append(synth.ExpressionMatrix(xh.numpy(), wh.numpy(), wl["genes"], wl["cells"]))
+        rh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
+        rh.copy_(wl["raw"])
+        host.append(rh.numpy())
+    wl["raw"] = None
+    params = wl["params"]
     torch.cuda.synchronize()
-    # a pipeline needs a few steps to show its steady state; the first timed step still uploads
-    # its matrices synchronously (its share shrinks with the number of steps)
     steps = max(args.steps, 12)
     warm = max(args.warmup, 3)
-    d2h = 0
+    dist_mode = world > 1
 
-    def one_step(data, nxt):
-        # this step's matrices first (a no-op when the previous step already started their
-        # upload), then the NEXT step's: queued on the copy engine right behind, so the engine
-        # never idles and never serves the later data set first
-        FP.prefetch(data.base, data.weights, replicated=world > 1)
+    trace = [] if os.environ.get("FP_BENCH_DEBUG") else None
+
+    def stamp(what):
+        if trace is not None:
+            trace.append((what, time.perf_counter()))
+
+    def one_step(raw, nxt):
+        stamp("begin")
+        FP.prefetch(raw, replicated=dist_mode)
         if nxt is not None:
-            FP.prefetch(nxt.base, nxt.weights, replicated=world > 1)
-        real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5, distributed=world > 1)
-        rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5, distributed=world > 1)
+            FP.prefetch(nxt, replicated=dist_mode)
+        raw_dev = E.expression_cache.get(raw, dist_mode)
+        w_dev = T.compute_weights(None, params, raw_dev)                       # Pipelines.py:120
+        x_dev = NM.row_normalization(raw_dev)                                  # Pipelines.py:202
+        data = synth.ExpressionMatrix(x_dev, w_dev, wl["genes"], wl["cells"])
+        stamp("prep issued")
+        real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5, distributed=dist_mode)
+        stamp("score real issued")
+        rnd = S.calculate_sig_scores(data, wl["rnd"], "weighted_avg", None, 5, distributed=dist_mode)
+        stamp("score rnd issued")
         res = S.sigs_vs_projections(wl["projections"], real, rnd, SIGMA, precision=precision,
-                                    distributed=world > 1)
+                                    distributed=dist_mode)
+        stamp("svp returned")
         first = next(iter(real.values()))
-        host_scores = first._batch.host_scores()                 # D2H of all real scores
-        E.expression_cache.evict(data.base)
-        E.expression_cache.evict(data.weights)
+        host_scores = first._batch.host_scores_local()           # D2H of this rank's real scores
+        FP.evict(raw)
+        stamp("scores on host")
         return real, rnd, host_scores.nbytes + res[2].nbytes + res[3].nbytes + res[4].nbytes
 
-    # warm-up steps (untimed, pipelined like the timed ones: they also grow the pinned staging
-    # pools and the allocator caches to their steady size), then everything resident is dropped
-    # and ``steps`` timed steps run back to back; every timed step's inputs cross PCIe inside the
-    # timed region (the first one synchronously, the others prefetched during the previous step)
     E.clear_device_cache()
     for it in range(warm):
-        real, rnd, d2h = one_step(host[it % len(host)], host[(it + 1) % len(host)] if it + 1 < warm else None)
+        real, rnd, d2h = one_step(host[it % 2], host[(it + 1) % 2] if it + 1 < warm else None)
     E.clear_device_cache()
     torch.cuda.synchronize()
-    if world > 1:
+    if dist_mode:
         dist.barrier()
     t0 = time.perf_counter()
     for it in range(steps):
-        data = host[it % len(host)]
-        nxt = host[(it + 1) % len(host)] if it + 1 < steps else None
-        real, rnd, d2h = one_step(data, nxt)
-        if os.environ.get("FP_BENCH_DEBUG"):
-            sys.stderr.write("e2e step %d done at %.1f ms\n" % (it, 1e3 * (time.perf_counter() - t0)))
+        real, rnd, d2h = one_step(host[it % 2], host[(it + 1) % 2] if it + 1 < steps else None)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    if world > 1:
-        tmax = torch.tensor([dt], dtype=torch.float64, device=device)
+    if trace is not None:
+        for (a, ta), (b, tb) in zip(trace[:-1], trace[1:]):
+            if b != "begin":
+                sys.stderr.write("e2e %-18s %7.2f ms\n" % (b, 1e3 * (tb - ta)))
+            else:
+                sys.stderr.write("e2e ---- step gap   %7.2f ms\n" % (1e3 * (tb - ta)))
+    tsum = torch.tensor([dt, float(d2h)], dtype=torch.float64, device=device)
+    if dist_mode:
+        tmax = tsum.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dt = float(tmax[0])
-    times = [dt / steps] * steps
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, d2h = float(tmax[0]), float(tsum[1])
     E.clear_device_cache()
-    t = sum(times) / len(times)
+    t = dt / steps
     n_rows = len(real) + len(rnd)
     nnz = sum(len(s.sig_dict) for s in wl["real"]) + sum(len(s.sig_dict) for s in wl["rnd"])
-    # X and W are one data set: every rank uploads 1/world of their rows (all-gathered over NVLink)
-    h2d = 2 * G * N * 8 + world * (nnz * 5 + (n_rows + 1) * 4 + P * 2 * N * 8)
-    return {"value": world * n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h) * world, "s_per_step": t, "steps": len(times),
-            "api": "Signatures.calculate_sig_scores x2 + Signatures.sigs_vs_projections(distributed=%s), "
-                   "pinned host inputs; steps back to back, the upload of the next step's matrices "
-                   "(fastproject_b200.prefetch at the start of the step) overlaps the current step%s"
-                   % (world > 1, "; the expression matrices are one data set per job: every rank uploads "
-                      "1/world of the rows over its PCIe link and the rows are all-gathered over NVLink"
-                      if world > 1 else "")}
+    # the raw matrix is one data set: every rank uploads 1/world of its rows (all-gathered over NVLink)
+    h2d = G * N * 8 + nnz * 5 + (n_rows + world) * 4 + world * (P * 2 * N * 8 + 4 * N * 8)
+    return {"value": n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "s_per_step": t, "steps": steps,
+            "api": "fastproject_b200.prefetch(raw) -> Transforms.compute_weights + NormalizationMethods."
+                   "row_normalization on the device -> Signatures.calculate_sig_scores x2 -> Signatures."
+                   "sigs_vs_projections(distributed=%s); pinned host input; steps back to back, the upload of "
+                   "the next step's matrix overlaps the current step%s"
+                   % (dist_mode, "; one job: every rank uploads 1/world of the rows over its PCIe link and the "
+                      "rows are all-gathered over NVLink" if dist_mode else "")}
 
 
 # ----------------------------------------------------------------------------
-# CPU arm (oracle port of the reference)
+# CPU legs
 # ----------------------------------------------------------------------------
-def cpu_baseline(cfg, wl, budget_s=25.0, host=None):
-    """Times the NumPy/SciPy restatement of the reference (oracle/fp_oracle.py)
-    on a bounded sample and scales linearly to the full workload:
-      scoring : the first S signatures on the full G x N matrices (cost is
-                linear in the number of signatures);
-      ranks   : scipy rankdata on S2 columns;
-      consistency : ONE projection, a block of B rows of the N x N kernel
-                against ALL K+R rank columns, with the row-blocked restatement
-                (rows are independent and equal in cost -> x N/B x P);
-      median  : np.median on the block's dissimilarities, scaled the same way.
-    """
-    import numpy as np
-    from oracle import fp_oracle as O
-    G, N, P = cfg["G"], cfg["N"], cfg["P"]
+def cpu_whole_job(cfg, wl, host=None):
+    """ONE WHOLE job on the host cores: the installed reference (kind "reference") or the port.
+    Returns (cpu_baseline dict, the finished CpuJob)."""
+    from oracle import cpu_job as J
+    P = cfg["P"]
     if host is None:
-        xh = wl["x"].cpu().numpy()
-        wh = wl["w"].cpu().numpy()
+        xh, wh = wl["x"].cpu().numpy(), wl["w"].cpu().numpy()
     else:
         xh, wh = host
-    odata = O.ExpressionMatrix(xh, wh, wl["genes"], wl["cells"])
+    job = J.CpuJob(xh, wh, wl["genes"], wl["cells"], wl["projections"], wl["real"], wl["rnd"], SIGMA, 5)
+    with J.blas_threads() as threads:
+        t0 = time.perf_counter()
+        job.run()
+        dt = time.perf_counter() - t0
+    n_rows = len(job.real) + len(job.rnd)
+    return ({"value": n_rows * P / dt, "unit": "pairs/s", "cores": threads or os.cpu_count(),
+             "kind": job.kind, "seconds_whole_job": dt, "seconds_by_stage": job.seconds,
+             "scores_per_sec": cfg["N"] * n_rows / max(job.seconds["score"], 1e-9),
+             "sample": "one WHOLE job, not a sample: %s -- calculate_sig_scores on all %d signatures "
+                       "(single-threaded Python/NumPy, as the reference is), SignatureScores.ranks, "
+                       "sigs_vs_projections over all %d projections; BLAS threads = %s of %d host cores"
+                       % ("the unmodified reference (baseline/_ref)" if job.kind == "reference"
+                          else "oracle port (row-blocked N x N kernel)", n_rows, P, threads, os.cpu_count() or 0)},
+            job)
+
+
+def cpu_sampled(cfg, wl, budget_s=25.0):
+    """For shapes whose whole job takes the host hours (C3): the oracle port on a bounded sample,
+    scaled linearly -- scoring on S signatures of the full matrices; rankdata on the same;
+    consistency: ONE projection, a block of rows of the N x N kernel against ALL K+R rank columns
+    (rows are independent and equal in cost); np.median on 64 columns."""
+    import numpy as np
+    from oracle import fp_oracle as O, cpu_job as J
+    G, N, P = cfg["G"], cfg["N"], cfg["P"]
+    sample = wl["real"][:12] + wl["rnd"][::max(1, len(wl["rnd"]) // 36)][:36]
+    gene_pos = dict((g, i) for i, g in enumerate(wl["genes"]))
+    rows = sorted(set(gene_pos[g] for s in sample for g in s.sig_dict if g in gene_pos))
+    import torch
+    idx = torch.tensor(rows, dtype=torch.long, device=wl["x"].device)
+    # only the gene rows the sampled signatures use cross to the host (the per-signature cost of
+    # the reference's evaluator does not depend on the rows it does not touch, beyond sig_indices)
+    xh, wh = wl["x"].index_select(0, idx).cpu().numpy(), wl["w"].index_select(0, idx).cpu().numpy()
+    odata = O.ExpressionMatrix(xh, wh, [wl["genes"][r] for r in rows], wl["cells"])
     to_o = lambda s: O.Signature(s.sig_dict, s.signed, s.source, s.name)
-    sample_sigs = [to_o(s) for s in (wl["real"][:24] + wl["rnd"][::max(1, len(wl["rnd"]) // 72)][:72])]
-    t0 = time.perf_counter()
-    res = O.calculate_sig_scores(odata, sample_sigs, "weighted_avg", None, 5)
-    t_score = (time.perf_counter() - t0) / max(1, len(res))
-    n_rows = len(wl["real"]) + len(wl["rnd"])
-    t0 = time.perf_counter()
-    rk = np.array([res[k].ranks for k in res])
-    t_rank = (time.perf_counter() - t0) / max(1, len(res))
-    # rank matrix of the full width: tile the sample's ranks (values do not change the cost)
-    reps = (n_rows + rk.shape[0] - 1) // rk.shape[0]
-    ranks = np.ascontiguousarray(np.tile(rk, (reps, 1))[:n_rows].T)        # N x (K+R)
-    coords = wl["projections"][sorted(wl["projections"].keys())[0]]
-    B = 512 if N >= 4096 else N
-    # calibrate block size to the budget
-    t0 = time.perf_counter()
-    wt = O.neighbourhood_weights(coords, SIGMA, slice(0, B))
-    dis = np.abs(ranks[:B] - np.dot(wt, ranks))
-    t_blk = time.perf_counter() - t0
-    rows_done = B
-    while rows_done < N and (time.perf_counter() - t0) < budget_s * 0.6:
-        lo = rows_done
-        hi = min(N, lo + B)
-        wt = O.neighbourhood_weights(coords, SIGMA, slice(lo, hi))
-        dis = np.abs(ranks[lo:hi] - np.dot(wt, ranks))
-        rows_done = hi
-    t_cons_rows = (time.perf_counter() - t0) / rows_done                   # per row, one projection
-    t0 = time.perf_counter()
-    cols = min(n_rows, 64)
-    full_col = np.abs(np.random.RandomState(0).normal(size=(N, cols)))
-    np.median(full_col, axis=0)
-    t_med = (time.perf_counter() - t0) / cols
+    with J.blas_threads() as threads:
+        t0 = time.perf_counter()
+        res = O.calculate_sig_scores(odata, [to_o(s) for s in sample], "weighted_avg", None, 5)
+        t_score = (time.perf_counter() - t0) / max(1, len(res))
+        n_rows = len(wl["real"]) + len(wl["rnd"])
+        t0 = time.perf_counter()
+        rk = np.array([res[k].ranks for k in res])
+        t_rank = (time.perf_counter() - t0) / max(1, len(res))
+        reps = (n_rows + rk.shape[0] - 1) // rk.shape[0]
+        ranks = np.ascontiguousarray(np.tile(rk, (reps, 1))[:n_rows].T)        # N x (K+R)
+        coords = wl["projections"][sorted(wl["projections"].keys())[0]]
+        B = 256
+        t0 = time.perf_counter()
+        rows_done = 0
+        while rows_done < N and (rows_done == 0 or (time.perf_counter() - t0) < budget_s * 0.6):
+            lo, hi = rows_done, min(N, rows_done + B)
+            wt = O.neighbourhood_weights(coords, SIGMA, slice(lo, hi))
+            np.abs(ranks[lo:hi] - np.dot(wt, ranks))
+            rows_done = hi
+        t_cons_rows = (time.perf_counter() - t0) / rows_done
+        t0 = time.perf_counter()
+        cols = min(n_rows, 16)
+        np.median(np.abs(np.random.RandomState(0).normal(size=(N, cols))), axis=0)
+        t_med = (time.perf_counter() - t0) / cols
     t_full = n_rows * (t_score + t_rank) + P * (N * t_cons_rows + n_rows * t_med)
-    return {"value": n_rows * P / t_full, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-            "scores_per_sec": N / t_score,
-            "sample": "oracle port (NumPy/SciPy float64, BLAS threads = all %d cores): scoring on %d "
-                      "signatures; rankdata on the same; consistency on %d of %d rows of 1 of %d "
-                      "projections against all %d signature columns (row-blocked restatement); "
-                      "np.median on %d columns; scaled linearly to the full workload "
-                      "(%.1f s extrapolated per step)" % (os.cpu_count() or 0, len(res), rows_done, N,
-                                                          P, n_rows, cols, t_full),
-            "extrapolated_s_per_step": t_full}
+    return {"value": n_rows * P / t_full, "unit": "pairs/s", "cores": threads or os.cpu_count(), "kind": "port",
+            "scores_per_sec": N / t_score, "extrapolated_s_per_step": t_full,
+            "sample": "EXTRAPOLATED (the whole job would take the host %.0f s): oracle port, scoring + rankdata on "
+                      "%d signatures; consistency on %d of %d rows of 1 of %d projections against all %d "
+                      "signature columns; np.median on %d columns; scaled linearly"
+                      % (t_full, len(res), rows_done, N, P, n_rows, cols)}
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores.  Rank 0 only.
+    The K timed steps are K consecutive slices of ONE whole job (a step is 1/K of the job); the W
+    warm-up steps run slices of a small job of the same kind."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
-    from fastproject_b200 import Signatures as S, synth
+    from fastproject_b200 import synth
+    from oracle import cpu_job as J
     cfg = WORKLOADS[args.workload]
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
     x, w, z, genes, cells = synth.make_expression(G, N)
-    projections, _ = synth.make_projections(N, P, seed=1335607829)
-    defs = synth.make_signature_dicts(genes, cfg["K"], seed=1335607830)
-    import random
-    random.seed(1335607828); np.random.seed(1335607828 % 2 ** 32)
-    wl = dict(genes=genes, cells=cells, projections=projections,
-              real=[S.Signature(d, sg, "synthetic", nm) for nm, d, sg in defs],
-              rnd=S.generate_random_sigs(genes, False, SIZES, cfg["R_PER_SIZE"]))
-    vals = []
-    last = None
-    for it in range(args.warmup + args.steps):
-        budget = 20.0 if it >= args.warmup else 5.0
-        last = cpu_baseline(cfg, wl, budget_s=budget, host=(x, w))
-        if it >= args.warmup:
-            vals.append(last["value"])
-    value = sum(vals) / len(vals)
-    n_rows = len(wl["real"]) + len(wl["rnd"])
-    out = {"impl": "reference",
-           "metric": "signature x projection consistency pairs/sec (full hot path: score + rank + "
-                     "consistency + median + p-values)",
-           "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * n_rows * P / value, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": describe_config(args.workload, cfg, len(wl["real"]), len(wl["rnd"]),
-                                     args.precision or ("tc" if N <= 4000000 else "fp64"), args.gpus),
-           "cpu_baseline": dict(last, value=value),
+    del z
+    projections, _ = synth.make_projections(N, P, seed=SEED + 1)
+    real, rnd = make_signatures(cfg, genes)
+    whole_feasible = args.workload in ("C2", "tiny")
+    if not whole_feasible:
+        wl = dict(genes=genes, cells=cells, projections=projections, real=real, rnd=rnd)
+        emit_reference(args, cfg, real, rnd, None, sampled=(x, w, wl))
+        return
+    with J.blas_threads() as threads:
+        if args.warmup:
+            n_small = min(N, 2048)
+            small_proj = dict((k, synth.unit_radius(v[:, :n_small].T)) for k, v in list(projections.items())[:2])
+            warm = J.CpuJob(np.ascontiguousarray(x[:, :n_small]), np.ascontiguousarray(w[:, :n_small]), genes,
+                            cells[:n_small], small_proj, real[:40], rnd[:200], SIGMA, 5, split_projections=True)
+            for lo, hi in warm.step_bounds(args.warmup):
+                warm.run(lo, hi)
+            del warm
+        job = J.CpuJob(x, w, genes, cells, projections, real, rnd, SIGMA, 5, split_projections=True)
+        t0 = time.perf_counter()
+        for lo, hi in job.step_bounds(args.steps):
+            job.run(lo, hi)
+        dt = time.perf_counter() - t0
+    emit_reference(args, cfg, real, rnd, dict(dt=dt, job=job, threads=threads))
+
+
+def emit_reference(args, cfg, real, rnd, whole, sampled=None):
+    P, N = cfg["P"], cfg["N"]
+    if whole is not None:
+        job, dt = whole["job"], whole["dt"]
+        n_rows = len(job.real) + len(job.rnd)
+        value = n_rows * P / dt
+        base = {"value": value, "unit": "pairs/s", "cores": whole["threads"] or os.cpu_count(), "kind": job.kind,
+                "seconds_whole_job": dt, "seconds_by_stage": job.seconds,
+                "scores_per_sec": N * n_rows / max(job.seconds["score"], 1e-9),
+                "sample": "%d steps = %d consecutive slices of ONE whole job (%d units: calculate_sig_scores on "
+                          "chunks of 50 signatures + their ranks, then sigs_vs_projections per projection), %s; "
+                          "BLAS threads = %s of %d host cores; scoring is single-threaded Python/NumPy as in the "
+                          "reference" % (args.steps, args.steps, len(job.units),
+                                         "the unmodified reference (baseline/_ref)" if job.kind == "reference"
+                                         else "oracle port (row-blocked N x N kernel)",
+                                         whole["threads"], os.cpu_count() or 0)}
+        ms_step = 1e3 * dt / args.steps
+    else:
+        x, w, wl = sampled
+        import torch
+        wl = dict(wl, x=torch.from_numpy(x), w=torch.from_numpy(w))
+        base = cpu_sampled(cfg, wl, budget_s=20.0 * max(1, args.steps) / 3)
+        n_rows = len(real) + len(rnd)
+        value = base["value"]
+        ms_step = 1e3 * n_rows * P / value
+    precision = args.precision or "tc"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": describe_config(args.workload, cfg, len(real), len(rnd), precision, args.gpus),
+           "cpu_baseline": base,
            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)

@@ -131,7 +131,8 @@ def to_device_replicated(arr):
         mine[:hi - lo].copy_(host[lo:hi], non_blocking=True)
     if hi - lo < rows_per:
         mine[hi - lo:].zero_()
-    dist.all_gather_into_tensor(full, mine.clone() if world > 1 else mine)
+    from . import distributed as D
+    D.all_gather_into(full, mine.clone())
     return full[:rows]
 
 

@@ -91,6 +91,18 @@ def all_reduce_sum(t, group=None):
     return t
 
 
+def all_gather_into(buf, mine, group=None):
+    """``dist.all_gather_into_tensor`` that also works for CUDA tensors on a gloo group (the
+    two-ranks-on-one-GPU test): staged through the host there."""
+    if _is_gloo_cuda(mine, group):
+        hb = torch.empty(buf.shape, dtype=buf.dtype)
+        dist.all_gather_into_tensor(hb, mine.cpu(), group=group)
+        buf.copy_(hb)
+    else:
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    return buf
+
+
 def even_bounds(n_rows, world_size):
     return [shard_bounds(n_rows, world_size, r) for r in range(world_size)]
 
@@ -111,12 +123,7 @@ def all_gather_row_blocks(local, bounds, group=None):
         mine[:local.shape[0]] = local
     mine = mine.contiguous()
     buf = torch.empty((world_size * widest, ld), dtype=local.dtype, device=local.device)
-    if _is_gloo_cuda(local, group):
-        hb = torch.empty(buf.shape, dtype=buf.dtype)
-        dist.all_gather_into_tensor(hb, mine.cpu(), group=group)
-        buf.copy_(hb)
-    else:
-        dist.all_gather_into_tensor(buf, mine, group=group)
+    all_gather_into(buf, mine, group)
     if all(w == widest for w in widths):
         return buf
     return torch.cat([buf[r * widest:r * widest + widths[r]] for r in range(world_size)], dim=0)
