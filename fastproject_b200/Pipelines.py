@@ -3,10 +3,13 @@
 signature x projection matrices to the significant signatures (``Analysis``, :299-349).
 "Next" row N4 of SURVEY.md 8f; host code (the matrices are signatures x projections).
 
-PARITY UNPINNED: in the reference this is an inline block of ``Analysis()`` and it no longer
-runs on the pandas of this image (``Series[int]`` on a string index meant "by position" when it
-was written and raises ``KeyError`` now), so no golden output can be produced from the live
-reference.  The function below restates the block with the positional meaning spelled out.
+Parity: pinned.  In the reference this is an inline block of ``Analysis()``; it runs on this
+image's pandas once ``Series[int]`` on a label index means "by position" again (what it meant
+when the block was written).  ``tests/config1/run_config1.py golden`` runs the UNMODIFIED
+reference pipeline with that shim and records what enters and leaves the block; the goldens
+``tests/golden/case_filter_small.npz`` (260 samples, 262 signatures: the -1.3 threshold raised to
+the 200th best value) and ``case_filter_large.npz`` (2 050 samples: the 200 best signatures) are
+reproduced exactly by the functions below (``tests/test_host_logic.py``).
 """
 from __future__ import annotations
 

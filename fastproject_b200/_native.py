@@ -24,6 +24,7 @@ SIGNATURES = {
     "fp_version": (ctypes.c_char_p, []),
     "fp_last_error": (ctypes.c_char_p, []),
     "fp_launch_count": (ctypes.c_uint64, []),
+    "fp_match_labels": (c_int, [ctypes.c_char_p, c_i64, c_i64, ctypes.c_char_p, c_i64, c_i64, c_ptr]),
     "fp_gene_detected_mean": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     "fp_score_signatures": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
                                     c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),

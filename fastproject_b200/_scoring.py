@@ -64,33 +64,62 @@ def signature_rows(sig_dict, index):
     return rows, signs
 
 
+def _match_rows(flat_genes, n_entries, row_labels):
+    """Rows of the named genes (-1: not on the matrix) through the library's host-side hash
+    table (``fp_match_labels``); None when the labels are duplicated or are not plain strings
+    (the caller then takes the per-signature path)."""
+    from . import _native
+    try:
+        labels = "\0".join(row_labels).encode("utf-8")
+        queries = "\0".join(flat_genes).encode("utf-8")
+    except TypeError:
+        return None
+    rows = np.empty(n_entries, dtype=np.int32)
+    rc = _native.load().fp_match_labels(labels, len(labels), len(row_labels), queries, len(queries),
+                                        n_entries, rows.ctypes.data)
+    if rc != 0:
+        return None
+    return rows
+
+
+def _signs_of(flat_vals):
+    """+1 for a dict value equal to 1 or 0, -1 for -1, 0 (= ignored) for anything else
+    (Signatures.py:750-753); None if the values are not numbers."""
+    kinds = set(flat_vals)
+    try:
+        if kinds <= {1, 0}:                       # unsigned lists, every random background list
+            return np.ones(len(flat_vals), dtype=np.int8)
+        if kinds <= {1, 0, -1}:
+            v = np.frombuffer(bytes(map((1).__add__, flat_vals)), dtype=np.uint8).astype(np.int8) - 1
+            return np.where(v == 0, 1, v).astype(np.int8)
+        vals = np.fromiter(flat_vals, dtype=np.float64, count=len(flat_vals))
+    except (TypeError, ValueError):
+        return None
+    return np.where((vals == 1) | (vals == 0), 1, np.where(vals == -1, -1, 0)).astype(np.int8)
+
+
 def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject=False):
     """list[Signature] -> (kept positions, sig_ptr, sig_gene, sig_sign, num_genes).
     Signatures with no matched gene, or fewer than ``min_signature_genes``, are
     rejected -- the reference raises ValueError for them
     (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676).
 
-    All signatures are matched in one vectorised pass (C-level ``map`` over the
-    concatenated gene lists, one ``lexsort``); duplicated row labels take the
-    per-signature path."""
-    index = gene_row_index(row_labels)
-    if len(index) != len(row_labels) or raise_on_reject or len(signatures) < 8:
-        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+    All signatures are matched in one pass: the gene names of the whole list go to the
+    library's host-side hash table as one NUL-separated blob (no Python object per gene), one
+    sort orders the entries by (signature, gene row); duplicated row labels and non-string
+    names take the per-signature path."""
+    if raise_on_reject or len(signatures) < 8:
+        return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
     dicts = [sig.sig_dict for sig in signatures]
     lengths = np.fromiter((len(d) for d in dicts), dtype=np.int64, count=len(dicts))
-    flat_genes = list(itertools.chain.from_iterable(dicts))
+    n_entries = int(lengths.sum())
     flat_vals = list(itertools.chain.from_iterable(d.values() for d in dicts))
-    try:                                   # one C call when every gene is on the matrix
-        rows = np.array(operator.itemgetter(*flat_genes)(index), dtype=np.int64).reshape(-1)
-    except (KeyError, TypeError):          # a gene that is not on the matrix / no genes at all
-        rows = np.fromiter(map(index.get, flat_genes, itertools.repeat(-1)), dtype=np.int64,
-                           count=len(flat_genes))
-    try:
-        vals = np.fromiter(flat_vals, dtype=np.float64, count=len(flat_vals))
-    except (TypeError, ValueError):
-        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
-    # a dict value equal to 1 or 0 counts as +1, equal to -1 as -1, anything else is ignored
-    signs = np.where((vals == 1) | (vals == 0), 1, np.where(vals == -1, -1, 0)).astype(np.int8)
+    rows = _match_rows(itertools.chain.from_iterable(dicts), n_entries, row_labels) if n_entries else \
+        np.zeros(0, dtype=np.int32)
+    signs = _signs_of(flat_vals) if rows is not None else None
+    if rows is None or signs is None:
+        return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
+    rows = rows.astype(np.int64)
     sig_id = np.repeat(np.arange(len(dicts), dtype=np.int64), lengths)
     ok = (rows >= 0) & (signs != 0)
     if not ok.all():
@@ -108,15 +137,14 @@ def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject
     key.sort()
     signs = ((key & 1) * 2 - 1).astype(np.int8)
     rows = (key >> 1) % n_rows_total
-    order = slice(None)
     kept = np.nonzero(keep_sig)[0]
     counts = counts_all[kept]
     ptr = np.zeros(len(kept) + 1, dtype=np.int64)
     np.cumsum(counts, out=ptr[1:])
     if ptr[-1] >= 2 ** 31:
         raise ValueError("signature membership table exceeds int32 indexing")
-    return ([int(k) for k in kept], ptr.astype(np.int32), rows[order].astype(np.int32),
-            signs[order].astype(np.int8), counts)
+    return ([int(k) for k in kept], ptr.astype(np.int32), rows.astype(np.int32),
+            signs.astype(np.int8), counts)
 
 
 def _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject=False):
@@ -259,7 +287,8 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
         from . import distributed as D
         by_pos = np.zeros(len(signatures), dtype=np.int64)
         by_pos[np.asarray(kept, dtype=np.int64) + pos_lo] = counts
-        by_pos = D.all_reduce_sum(_engine.to_device(by_pos, torch.int64)).cpu().numpy()
+        # through the host (gloo) group: the launch queue of the GPU keeps running meanwhile
+        by_pos = D.all_reduce_sum_host(by_pos)
         all_kept = np.nonzero(by_pos)[0]
         bounds = []
         for r in range(world_size):

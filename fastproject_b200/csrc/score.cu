@@ -9,7 +9,7 @@
 // evaluates row after row (sequential in g).  Every product below is a
 // separately rounded __dmul_rn and every accumulation a __dadd_rn in ascending
 // gene order, so no FMA contraction or reassociation can change a bit.
-#include "fp_common.cuh"
+#include "row_tree.cuh"
 
 namespace {
 
@@ -134,8 +134,6 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
 }
 
 // mu_g over all cells, NumPy pairwise order (SigScoreMethods.py:109-111).
-// One block per gene: each thread reduces whole <=128-element leaves of the
-// pairwise tree, leaf sums are then combined in tree order by one thread.
 struct DetectedProduct {
     const double *x, *z;
     __device__ double operator()(long i) const { return __dmul_rn(x[i], __dsub_rn(1.0, z[i])); }
@@ -145,11 +143,47 @@ struct DetectedCount {
     __device__ double operator()(long i) const { return __dsub_rn(1.0, z[i]); }
 };
 
-__global__ void gene_detected_mean_kernel(const double *__restrict__ X, const double *__restrict__ Z,
-                                          long G, long N, long ld, double *__restrict__ out_mu) {
-    // One warp-lane per gene keeps the recursion trivially exact; genes are
-    // spread over lanes so that the whole grid covers G.  This step is O(G*N)
-    // reads and runs once per data set (only for the "imputed" method).
+// One CTA per gene (persistent over the genes): the CTA enumerates the pairwise tree of a row of
+// N cells once into shared memory, then, per gene, eight lanes sum each <= 128-element leaf
+// (lane k owns NumPy's k-th interleaved accumulator: coalesced 64-byte loads, rowtree::leaf_sums)
+// and one thread folds the leaf sums with the tree's post-order program -- NumPy's
+// add.reduce(axis=1) bit for bit, as normalize.cu and weights.cu do it.
+constexpr int MU_THREADS = 256;
+
+__global__ void __launch_bounds__(MU_THREADS)
+gene_detected_mean_kernel(const double *__restrict__ X, const double *__restrict__ Z, long G, long N, long ld,
+                          int max_leaves, double *__restrict__ out_mu) {
+    extern __shared__ __align__(16) unsigned char mu_smem[];
+    double *leaf_sum = reinterpret_cast<double *>(mu_smem);                               // max_leaves
+    fp::rowtree::Leaf *leaves = reinterpret_cast<fp::rowtree::Leaf *>(leaf_sum + max_leaves);
+    int *prog = reinterpret_cast<int *>(leaves + max_leaves);                              // 2 * max_leaves
+    __shared__ double stack[fp::rowtree::MAX_DEPTH];
+    __shared__ int counts[2];
+    __shared__ double num_s;
+    if (threadIdx.x == 0) fp::rowtree::build_tree_device(0, N, leaves, &counts[0], prog, &counts[1]);
+    __syncthreads();
+    const int n_leaves = counts[0], n_prog = counts[1];
+    for (long g = blockIdx.x; g < G; g += gridDim.x) {
+        const double *x = X + g * ld, *z = Z + g * ld;
+        fp::rowtree::leaf_sums(DetectedProduct{x, z}, leaves, n_leaves, leaf_sum);
+        __syncthreads();
+        if (threadIdx.x == 0) num_s = fp::rowtree::fold_tree(leaf_sum, prog, n_prog, stack);
+        __syncthreads();
+        fp::rowtree::leaf_sums(DetectedCount{z}, leaves, n_leaves, leaf_sum);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double den = fp::rowtree::fold_tree(leaf_sum, prog, n_prog, stack);
+            double mu = __ddiv_rn(num_s, den);
+            if (mu != mu) mu = 0.0;                  // mu[np.isnan(mu)] = 0.0
+            out_mu[g] = mu;
+        }
+        __syncthreads();
+    }
+}
+
+// rows too long for the tree to fit in shared memory (> ~1.2 M cells): one thread per gene
+__global__ void gene_detected_mean_long_kernel(const double *__restrict__ X, const double *__restrict__ Z,
+                                               long G, long N, long ld, double *__restrict__ out_mu) {
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     DetectedProduct prod{X + g * ld, Z + g * ld};
@@ -157,7 +191,7 @@ __global__ void gene_detected_mean_kernel(const double *__restrict__ X, const do
     const double num = fp::np_pairwise_sum(prod, 0, N);
     const double den = fp::np_pairwise_sum(cnt, 0, N);
     double mu = __ddiv_rn(num, den);
-    if (mu != mu) mu = 0.0;                      // mu[np.isnan(mu)] = 0.0
+    if (mu != mu) mu = 0.0;
     out_mu[g] = mu;
 }
 
@@ -169,10 +203,36 @@ extern "C" int fp_gene_detected_mean(const double *X, const double *Z, int64_t G
     FP_CHECK_ARG(X && Z && out_mu, "fp_gene_detected_mean: null pointer");
     FP_CHECK_ARG(G > 0 && N > 0 && ld >= N, "fp_gene_detected_mean: bad shape G=%ld N=%ld ld=%ld",
                  (long)G, (long)N, (long)ld);
+    // leaves of the pairwise tree of a row of N cells (the host enumeration only sizes the
+    // shared-memory tables; every CTA builds its own copy on the device)
+    long max_leaves = 1;
+    if (N < (1L << 31)) {
+        std::vector<fp::rowtree::Leaf> leaves;
+        std::vector<int> prog;
+        int depth = 0;
+        fp::rowtree::build_tree(0, N, leaves, prog, 1, depth);
+        max_leaves = (long)leaves.size();
+    }
+    const size_t smem = (size_t)max_leaves * (sizeof(double) + sizeof(fp::rowtree::Leaf) + 2 * sizeof(int));
+    if (N < (1L << 31) && smem <= 200 * 1024) {
+        static size_t smem_set = 0;
+        if (smem > 40 * 1024 && smem > smem_set) {
+            FP_CHECK_CUDA(cudaFuncSetAttribute(gene_detected_mean_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        long blocks = G;
+        const long cap = (long)fp::sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        gene_detected_mean_kernel<<<(unsigned)blocks, MU_THREADS, smem, fp::as_stream(stream)>>>(
+            X, Z, G, N, ld, (int)max_leaves, out_mu);
+        FP_CHECK_LAUNCH("gene_detected_mean_kernel");
+        return FP_OK;
+    }
     const int threads = 32;
-    gene_detected_mean_kernel<<<(unsigned)((G + threads - 1) / threads), threads, 0,
-                                fp::as_stream(stream)>>>(X, Z, G, N, ld, out_mu);
-    FP_CHECK_LAUNCH("gene_detected_mean_kernel");
+    gene_detected_mean_long_kernel<<<(unsigned)((G + threads - 1) / threads), threads, 0,
+                                     fp::as_stream(stream)>>>(X, Z, G, N, ld, out_mu);
+    FP_CHECK_LAUNCH("gene_detected_mean_long_kernel");
     return FP_OK;
 }
 

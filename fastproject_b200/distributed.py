@@ -103,6 +103,29 @@ def all_gather_into(buf, mine, group=None):
     return buf
 
 
+_host_group = None
+
+
+def host_group():
+    """A gloo group over the same ranks, for small HOST-side exchanges that must not wait for
+    (or be ordered behind) the work queued on the CUDA stream.  Created on first use: every rank
+    must reach that first use (``calculate_sig_scores(distributed=True)`` does)."""
+    global _host_group
+    if _host_group is None:
+        _host_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+    return _host_group
+
+
+def all_reduce_sum_host(arr):
+    """Sum of a small NumPy array over the ranks through the host group (no GPU involvement)."""
+    world_size, _ = world()
+    if world_size == 1:
+        return arr
+    t = torch.from_numpy(np.ascontiguousarray(arr).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=host_group())
+    return t.numpy()
+
+
 def even_bounds(n_rows, world_size):
     return [shard_bounds(n_rows, world_size, r) for r in range(world_size)]
 

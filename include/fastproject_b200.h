@@ -80,6 +80,19 @@ const char *fp_last_error(void);
 uint64_t    fp_launch_count(void);
 
 /*
+ * fp_match_labels -- HOST function (no device work): the row of every queried gene name among
+ * the matrix's row labels, or -1.  Both sides are NUL-separated UTF-8 blobs ("\0".join(...)):
+ * n_labels labels in labels_bytes bytes, n_queries names in queries_bytes bytes.  Replaces the
+ * label-probing loop of Signature.sig_indices (Signatures.py:738-753) for all signatures of a
+ * list at once.  Returns FP_OK; 1 if a row label occurs twice (the reference's loop then matches
+ * every such row -- the caller takes its per-signature path); FP_EINVAL if a blob does not hold
+ * the stated number of names (e.g. a name contains NUL).  out_rows_host: n_queries int32, host.
+ */
+int fp_match_labels(const char *labels, int64_t labels_bytes, int64_t n_labels,
+                    const char *queries, int64_t queries_bytes, int64_t n_queries,
+                    int32_t *out_rows_host);
+
+/*
  * fp_gene_detected_mean -- mu_g = sum_c x[g,c]*(1-z[g,c]) / sum_c (1-z[g,c]),
  * NaN -> 0.  Replaces SigScoreMethods.py:109-111 (imputed_eval_signature); the
  * row sums reproduce NumPy's pairwise summation order bit-for-bit.

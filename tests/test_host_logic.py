@@ -251,3 +251,82 @@ def test_nearest_neighbour_grid_search_rule():
         d = (x[:, None] - x[None, :]) ** 2 + (y[:, None] - y[None, :]) ** 2
         np.fill_diagonal(d, np.inf)
         assert np.array_equal(_grid_nearest_neighbour(x, y), d.min(axis=1))
+
+
+def test_fp_match_labels_host_function():
+    """The library's host-side label matcher (Signature.sig_indices, Signatures.py:738-753)."""
+    import __graft_entry__ as ge
+    ge.build()
+    from fastproject_b200 import _native, _scoring
+    lib = _native.load()
+
+    def match(labels, queries):
+        lb, qb = "\0".join(labels).encode("utf-8"), "\0".join(queries).encode("utf-8")
+        out = np.full(len(queries), -7, dtype=np.int32)
+        rc = lib.fp_match_labels(lb, len(lb), len(labels), qb, len(qb), len(queries), out.ctypes.data)
+        return rc, out
+
+    labels = ["ACTB", "", "Gene-é", "A", "AB", "actb"]
+    rc, rows = match(labels, ["AB", "ACTB", "missing", "", "Gene-é", "actb", "A", "ACT"])
+    assert rc == 0 and rows.tolist() == [4, 0, -1, 1, 2, 5, 3, -1]
+    rc, _ = match(["X", "Y", "X"], ["X"])
+    assert rc == 1                                      # duplicated row label: caller's slow path
+    rc, rows = match([], ["X", "Y"])
+    assert rc == 0 and rows.tolist() == [-1, -1]
+    lb = b"A\0B"
+    out = np.zeros(1, dtype=np.int32)
+    assert lib.fp_match_labels(lb, len(lb), 3, b"A", 1, 1, out.ctypes.data) == -1     # fewer labels than stated
+    assert lib.fp_match_labels(lb, len(lb), 1, b"A", 1, 1, out.ctypes.data) == -1     # more labels than stated
+    # the packer built on it: duplicated labels, odd values, non-string names all agree with the slow path
+    class Sig(object):
+        def __init__(self, d, name):
+            self.sig_dict, self.name = d, name
+    rng = np.random.RandomState(3)
+    genes = ["g%d" % i for i in range(60)]
+    sigs = [Sig(dict((genes[j], int(rng.choice([1, -1, 0]))) for j in rng.choice(60, 9, replace=False)), "s%d" % k)
+            for k in range(12)]
+    sigs[3].sig_dict["g5"] = 0.5                        # ignored value (weighted GMT entries)
+    sigs[4].sig_dict["nope"] = 1
+    for labels2 in (genes, genes[:30] + genes[:30], [str(g) for g in genes]):
+        fast = _scoring.pack_signatures(sigs, labels2, 3)
+        slow = _scoring._pack_signatures_slow(sigs, _scoring.gene_row_index(labels2), 3)
+        for a, b in zip(fast, slow):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+    sigs[5].sig_dict[17] = 1                            # a non-string name: falls back, same answer
+    fast = _scoring.pack_signatures(sigs, genes, 3)
+    slow = _scoring._pack_signatures_slow(sigs, _scoring.gene_row_index(genes), 3)
+    for a, b in zip(fast, slow):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.parametrize("case", ["case_filter_small", "case_filter_large"])
+def test_significance_filter_vs_reference_golden(case):
+    """Pipelines.Analysis' pruning of insignificant signatures (Pipelines.py:299-349).  The golden
+    files hold what went into that block (every sigs_vs_projections output) and what came out of
+    it in a run of the UNMODIFIED reference pipeline (tests/config1/run_config1.py golden, with the
+    pandas / open() shims listed there): small = 260 samples, 262 signatures (threshold -1.3 raised
+    to the 200th best value), large = more than 2000 samples (the 200 best signatures)."""
+    import os
+    from fastproject_b200 import Pipelines as P
+    path = os.path.join(os.path.dirname(__file__), "golden", case + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(case + " not generated")
+    d = np.load(path)
+
+    class Score(object):
+        def __init__(self, pre):
+            self.isPrecomputed = bool(pre)
+    model = dict(signatureScores=dict((str(n), Score(p)) for n, p in zip(d["sig_names"], d["sig_precomputed"])),
+                 projectionData=[])
+    n_calls = int(d["n_calls"])
+    for i in range(n_calls):
+        model["projectionData"].append(dict(signatureKeys=[str(k) for k in d["before_keys_%d" % i]],
+                                            sigProjMatrix=d["before_cons_%d" % i].copy(),
+                                            sigProjMatrix_p=d["before_logq_%d" % i].copy()))
+    keep = P.filter_significant_signatures(model, int(d["n_samples"]))
+    assert sum(keep.values()) < len(keep)               # the case does prune
+    for i in range(n_calls):
+        got = model["projectionData"][i]
+        assert got["signatureKeys"] == [str(k) for k in d["after_keys_%d" % i]]
+        assert np.array_equal(got["sigProjMatrix"], d["after_cons_%d" % i])
+        assert np.array_equal(got["sigProjMatrix_p"], d["after_logq_%d" % i])
