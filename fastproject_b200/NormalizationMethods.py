@@ -19,7 +19,7 @@ from . import _engine, _native
 
 def _to_dev(data):
     if isinstance(data, torch.Tensor) and data.is_cuda:
-        return data.to(torch.float64).contiguous(), True
+        return _engine.row_major(data), True
     return _engine.to_device(np.asarray(data, dtype=np.float64)), False
 
 

@@ -75,7 +75,7 @@ def compute_weights(fit_func, params, data, p_nd=None):
     _check_fit_func(fit_func)
     base = data.base if hasattr(data, "base") and not isinstance(data, (np.ndarray, torch.Tensor)) else data
     as_tensor = isinstance(base, torch.Tensor) and base.is_cuda
-    x = base.to(torch.float64).contiguous() if as_tensor else _engine.expression_cache.get(np.asarray(base))
+    x = _engine.row_major(base) if as_tensor else _engine.expression_cache.get(np.asarray(base))
     prm = params if isinstance(params, torch.Tensor) else np.asarray(params, dtype=np.float64)
     if tuple(prm.shape) != (4, x.shape[1]):
         raise ValueError("params must be 4 x Num_Samples (got %s for %d samples)" % (tuple(prm.shape), x.shape[1]))
@@ -88,7 +88,7 @@ def compute_weights(fit_func, params, data, p_nd=None):
         elif hasattr(p_nd, "values") and not isinstance(p_nd, torch.Tensor):
             p_nd = p_nd.values
         if isinstance(p_nd, torch.Tensor) and p_nd.is_cuda:
-            pnd_dev = p_nd.to(torch.float64).contiguous()
+            pnd_dev = _engine.row_major(p_nd)
         else:
             pnd_dev = _engine.to_device(np.asarray(p_nd, dtype=np.float64))
         if tuple(pnd_dev.shape) != tuple(x.shape):

@@ -36,6 +36,22 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+def alloc_matrix(g, n, device):
+    """[g x n] float64 view of a buffer whose row pitch is a multiple of 16 bytes (an even number of
+    doubles): what the TMA-staged scoring kernel needs of the matrices it streams."""
+    ld = int(n) + (int(n) & 1)
+    return torch.empty((int(g), ld), dtype=torch.float64, device=device)[:, :int(n)]
+
+
+def row_major(t):
+    """CUDA float64 matrix with unit column stride (any row pitch): as is; anything else: a
+    compact copy.  (``.contiguous()`` would repack a padded matrix to an odd pitch.)"""
+    t = t.to(torch.float64)
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
 TC_MAX_CELLS = 4000000   # FP_PRECISION_TC: three balanced base-256 digits of the centred values
 
 
@@ -100,6 +116,10 @@ def to_device(arr, dtype=torch.float64):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", UserWarning)     # read-only arrays: we only read them
             t = torch.from_numpy(a)
+    if t.dim() == 2 and dtype == torch.float64 and not t.is_cuda and (t.shape[1] & 1):
+        out = alloc_matrix(t.shape[0], t.shape[1], dev)           # odd row length: even pitch on the device
+        out.copy_(t, non_blocking=True)
+        return out
     t = t.to(device=dev, dtype=dtype, non_blocking=True)
     return t.contiguous()
 
@@ -124,16 +144,15 @@ def to_device_replicated(arr):
         host = torch.from_numpy(a)
     rows, cols = host.shape
     rows_per = (rows + world - 1) // world
-    full = torch.empty((world * rows_per, cols), dtype=torch.float64, device=dev)
+    ld = cols + (cols & 1)                                  # even row pitch (TMA-staged scoring)
+    full = torch.empty((world * rows_per, ld), dtype=torch.float64, device=dev)
     lo, hi = min(rows, rank * rows_per), min(rows, (rank + 1) * rows_per)
-    mine = full[rank * rows_per:(rank + 1) * rows_per]
+    mine = torch.zeros((rows_per, ld), dtype=torch.float64, device=dev)
     if hi > lo:
-        mine[:hi - lo].copy_(host[lo:hi], non_blocking=True)
-    if hi - lo < rows_per:
-        mine[hi - lo:].zero_()
+        mine[:hi - lo, :cols].copy_(host[lo:hi], non_blocking=True)
     from . import distributed as D
-    D.all_gather_into(full, mine.clone())
-    return full[:rows]
+    D.all_gather_into(full, mine)
+    return full[:rows, :cols]
 
 
 _PINNED_CHUNK = 32 << 20
@@ -221,7 +240,7 @@ class _ExpressionCache(object):
         the same host matrix; each rank then uploads 1/world of the rows over its own PCIe
         link and the rows are all-gathered over NVLink."""
         if isinstance(a, torch.Tensor) and a.is_cuda:
-            return a.to(torch.float64).contiguous()
+            return row_major(a)
         i = self._find(self._key(a))
         if i >= 0:
             entry = self.entries[i]
@@ -273,7 +292,7 @@ class _ExpressionCache(object):
                 # every rank issues its collectives in the same program order
                 t = to_device_replicated(host)
             else:
-                t = torch.empty(tuple(host.shape), dtype=torch.float64, device=dev)
+                t = alloc_matrix(host.shape[0], host.shape[1], dev)
                 t.copy_(host, non_blocking=True)
             done = torch.cuda.Event()
             done.record(_copy_stream)
@@ -340,21 +359,34 @@ def clear_device_cache():
 # --------------------------------------------------------------------------
 # kernels
 # --------------------------------------------------------------------------
-def score_signatures(method, x, w, z, sig_ptr, sig_gene, sig_sign, n_sigs):
+def score_signatures(method, x, w, z, sig_ptr, sig_gene, sig_sign, n_sigs, nnz=None):
     """x, w, z: G x N CUDA float64 (w / z may be None); CSR arrays on device.
+    ``nnz``: number of CSR entries when the host knows it (it always does: it built the CSR);
+    lets the library pick the TMA-staged kernel without reading ``sig_ptr`` back.
     Returns a [n_sigs x ld] CUDA tensor (ld = padded N)."""
     g, n = x.shape
     ld = padded(n)
     out = torch.zeros((n_sigs, ld), dtype=torch.float64, device=x.device)
     if n_sigs == 0:
         return out
+    # the kernels address X, W and Z with ONE row pitch
+    pitch = max(m.stride(0) for m in (x, w, z) if m is not None)
+    pitch += pitch & 1
+
+    def repitch(m):
+        if m is None or m.stride(0) == pitch:
+            return m
+        buf = torch.empty((g, pitch), dtype=torch.float64, device=m.device)[:, :n]
+        buf.copy_(m)
+        return buf
+    x, w, z = repitch(x), repitch(w), repitch(z)
     mu = None
     if method == "imputed":
         mu = torch.empty((g,), dtype=torch.float64, device=x.device)
         _native.call("fp_gene_detected_mean", ptr(x), ptr(z), g, n, x.stride(0), ptr(mu), stream_ptr())
     _native.call("fp_score_signatures", _native.METHOD_CODES[method], ptr(x), ptr(w), ptr(z),
                  g, n, x.stride(0), ptr(sig_ptr), ptr(sig_gene), ptr(sig_sign), n_sigs,
-                 ptr(mu), ptr(out), ld, stream_ptr())
+                 int(sig_gene.shape[0]) if nnz is None else int(nnz), ptr(mu), ptr(out), ld, stream_ptr())
     return out
 
 
@@ -373,10 +405,11 @@ def rank_rows(scores, n, method=_native.RANK_AVERAGE):
 def normalize_rows(x):
     """[G x N] CUDA float64 -> per-row z-scores (NumPy summation order), new tensor."""
     g, n = x.shape
-    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
+    out = alloc_matrix(g, n, x.device)
     nbytes = _native.query("fp_normalize_rows_workspace_bytes", n)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
-    _native.call("fp_normalize_rows", ptr(x), g, n, x.stride(0), ptr(out), n, ptr(ws), nbytes, stream_ptr())
+    _native.call("fp_normalize_rows", ptr(x), g, n, x.stride(0), ptr(out), out.stride(0), ptr(ws), nbytes,
+                 stream_ptr())
     return out
 
 
@@ -384,20 +417,20 @@ def compute_weights(x, params, p_nd=None):
     """[G x N] CUDA float64 expression, [4 x N] logistic parameters (x0, a, L, S), optional
     [G x N] probability of non-detection (None: the zero mask) -> [G x N] weights."""
     g, n = x.shape
-    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
+    out = alloc_matrix(g, n, x.device)
     params = params.contiguous()
     nbytes = _native.query("fp_compute_weights_workspace_bytes", n)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
     _native.call("fp_compute_weights", ptr(x), ptr(p_nd), ptr(params), g, n, x.stride(0),
-                 0 if p_nd is None else p_nd.stride(0), ptr(out), n, ptr(ws), nbytes, stream_ptr())
+                 0 if p_nd is None else p_nd.stride(0), ptr(out), out.stride(0), ptr(ws), nbytes, stream_ptr())
     return out
 
 
 def normalize_cols(x):
     """[G x N] CUDA float64 -> per-column z-scores (sequential row order), new tensor."""
     g, n = x.shape
-    out = torch.empty((g, n), dtype=torch.float64, device=x.device)
-    _native.call("fp_normalize_cols", ptr(x), g, n, x.stride(0), ptr(out), n, stream_ptr())
+    out = alloc_matrix(g, n, x.device)
+    _native.call("fp_normalize_cols", ptr(x), g, n, x.stride(0), ptr(out), out.stride(0), stream_ptr())
     return out
 
 

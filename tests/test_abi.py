@@ -39,14 +39,14 @@ def test_ctypes_table_matches_header(lib):
 
 
 def test_version_and_error_text(lib):
-    assert lib.fp_abi_version() == 1
+    assert lib.fp_abi_version() == 2
     assert b"sm_100a" in lib.fp_version()
     assert isinstance(lib.fp_last_error(), bytes)
 
 
 def test_argument_validation_without_gpu(lib):
     # bad arguments are rejected before any CUDA call is made
-    rc = lib.fp_score_signatures(99, None, None, None, 1, 1, 1, None, None, None, 0, None, None, 1, None)
+    rc = lib.fp_score_signatures(99, None, None, None, 1, 1, 1, None, None, None, 0, 0, None, None, 1, None)
     assert rc == -1 and b"unknown method" in lib.fp_last_error()
     rc = lib.fp_row_medians(None, 1, 1, 1, None, None)
     assert rc == -1
