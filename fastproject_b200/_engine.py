@@ -384,9 +384,12 @@ def score_signatures(method, x, w, z, sig_ptr, sig_gene, sig_sign, n_sigs, nnz=N
     if method == "imputed":
         mu = torch.empty((g,), dtype=torch.float64, device=x.device)
         _native.call("fp_gene_detected_mean", ptr(x), ptr(z), g, n, x.stride(0), ptr(mu), stream_ptr())
+    nnz = int(sig_gene.shape[0]) if nnz is None else int(nnz)
+    nbytes = _native.query("fp_score_workspace_bytes", g, n_sigs, nnz)
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
     _native.call("fp_score_signatures", _native.METHOD_CODES[method], ptr(x), ptr(w), ptr(z),
-                 g, n, x.stride(0), ptr(sig_ptr), ptr(sig_gene), ptr(sig_sign), n_sigs,
-                 int(sig_gene.shape[0]) if nnz is None else int(nnz), ptr(mu), ptr(out), ld, stream_ptr())
+                 g, n, x.stride(0), ptr(sig_ptr), ptr(sig_gene), ptr(sig_sign), n_sigs, nnz, ptr(mu), ptr(out), ld,
+                 ptr(ws), nbytes, stream_ptr())
     return out
 
 

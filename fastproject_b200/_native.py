@@ -26,8 +26,9 @@ SIGNATURES = {
     "fp_launch_count": (ctypes.c_uint64, []),
     "fp_match_labels": (c_int, [ctypes.c_char_p, c_i64, c_i64, ctypes.c_char_p, c_i64, c_i64, c_ptr]),
     "fp_gene_detected_mean": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "fp_score_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "fp_score_signatures": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
-                                    c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+                                    c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_size, c_ptr]),
     "fp_rank_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "fp_rank_columns": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
     "fp_rank_columns_ex": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_size, c_int, c_ptr]),

@@ -240,23 +240,28 @@ extern "C" int fp_gene_detected_mean(const double *X, const double *Z, int64_t G
 }
 
 // score_staged.cu
+size_t fp_score_staged_workspace_bytes(long G, long K, long nnz);
 bool fp_score_staged_applies(const double *X, const double *W, const double *Z, long G, long N, long ld, long K,
-                             long nnz);
+                             long nnz, bool forced);
 int fp_score_staged(int method, const double *X, const double *W, const double *Z, long G, long N, long ld,
-                    const int32_t *sig_ptr, const int32_t *sig_gene, const int8_t *sig_sign, long K,
-                    const double *gene_mu, double *out, long ld_out, cudaStream_t st);
+                    const int32_t *sig_ptr, const int32_t *sig_gene, const int8_t *sig_sign, long K, long nnz,
+                    const double *gene_mu, double *out, long ld_out, void *workspace, cudaStream_t st);
+
+extern "C" size_t fp_score_workspace_bytes(int64_t G, int64_t K, int64_t nnz) {
+    return fp_score_staged_workspace_bytes((long)G, (long)K, (long)nnz);
+}
 
 extern "C" int fp_score_signatures(int method, const double *X, const double *W, const double *Z,
                                    int64_t G, int64_t N, int64_t ld, const int32_t *sig_ptr,
                                    const int32_t *sig_gene, const int8_t *sig_sign, int64_t K, int64_t nnz,
                                    const double *gene_mu, double *out_scores, int64_t ld_out,
-                                   void *stream) {
+                                   void *workspace, size_t workspace_bytes, void *stream) {
     fp::clear_error();
     FP_CHECK_ARG(method >= FP_METHOD_NAIVE && method <= FP_METHOD_NONZERO,
                  "fp_score_signatures: unknown method %d", method);
     FP_CHECK_ARG(X && sig_ptr && sig_gene && sig_sign && out_scores,
                  "fp_score_signatures: null pointer");
-    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N && K >= 0,
+    FP_CHECK_ARG(G > 0 && N > 0 && ld >= N && ld_out >= N && K >= 0 && nnz >= 0,
                  "fp_score_signatures: bad shape G=%ld N=%ld ld=%ld K=%ld ld_out=%ld", (long)G,
                  (long)N, (long)ld, (long)K, (long)ld_out);
     FP_CHECK_ARG(method == FP_METHOD_NAIVE || method == FP_METHOD_NONZERO || W,
@@ -265,20 +270,19 @@ extern "C" int fp_score_signatures(int method, const double *X, const double *W,
                  "fp_score_signatures: method %d needs Z", method);
     FP_CHECK_ARG(method != FP_METHOD_IMPUTED || gene_mu, "fp_score_signatures: imputed needs gene_mu");
     if (K == 0) return FP_OK;
-    // nnz > 0: the caller knows the membership count, and the TMA-staged kernel is used when it
-    // moves fewer bytes through L2 than the gathers would (score_staged.cu); FASTPROJECT_B200_SCORE
-    // = gather | staged forces one of them (tests compare the two bit for bit)
-    {
+    // With the membership count and a workspace the TMA-staged kernel is used when it moves fewer
+    // bytes through L2 than the gathers would (score_staged.cu); FASTPROJECT_B200_SCORE = gather |
+    // staged forces one of them (tests compare the two bit for bit)
+    if (nnz > 0 && workspace && workspace_bytes >= fp_score_staged_workspace_bytes((long)G, (long)K, (long)nnz)) {
         const char *force = getenv("FASTPROJECT_B200_SCORE");
         const bool want_gather = force && !strcmp(force, "gather");
         const bool want_staged = force && !strcmp(force, "staged");
         const bool use_w = method == FP_METHOD_WEIGHTED || method == FP_METHOD_IMPUTED;
         const bool use_z = method == FP_METHOD_NONZERO || method == FP_METHOD_IMPUTED;
-        const long nnz_eff = want_staged ? (1L << 60) : (long)nnz;
         if (!want_gather && fp_score_staged_applies(X, use_w ? W : nullptr, use_z ? Z : nullptr, (long)G, (long)N,
-                                                    (long)ld, (long)K, nnz_eff))
+                                                    (long)ld, (long)K, (long)nnz, want_staged))
             return fp_score_staged(method, X, W, Z, (long)G, (long)N, (long)ld, sig_ptr, sig_gene, sig_sign, (long)K,
-                                   gene_mu, out_scores, (long)ld_out, fp::as_stream(stream));
+                                   (long)nnz, gene_mu, out_scores, (long)ld_out, workspace, fp::as_stream(stream));
     }
     dim3 block(kCellsPerBlock, kSigsPerBlock);
     long cell_tiles = (N + kCellsPerBlock - 1) / kCellsPerBlock;

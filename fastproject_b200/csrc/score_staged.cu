@@ -56,12 +56,40 @@ struct StagedCfg {
     static constexpr int smem_bytes = stages * stage_bytes + 128;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Preparation (one thread per signature, once per call): the CSR entries re-expressed for the
+// staged kernel -- op[t] = (gene mod 256) | (sign < 0) << 8, and cut[sig][b] = first entry of
+// signature sig whose gene lies in gene block >= b (b = 0 .. n_blocks).  With them the hot loop
+// needs ONE 2-byte load per entry and ONE 4-byte load per (signature, gene block), none of them
+// dependent on a previous entry: the first version walked the raw CSR with a dependent
+// gene-index load per entry and per block visit and was latency bound at 18 ms (config 2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+score_prepare_kernel(const int32_t *__restrict__ sig_ptr, const int32_t *__restrict__ sig_gene,
+                     const int8_t *__restrict__ sig_sign, long K, int n_blocks, uint16_t *__restrict__ op,
+                     int32_t *__restrict__ cut) {
+    // rows K .. rows_padded-1 (thread slots without a signature) stay all zero: empty ranges
+    const long sig = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sig >= K) return;
+    const int beg = sig_ptr[sig], end = sig_ptr[sig + 1];
+    int32_t *row = cut + sig * (n_blocks + 1);
+    int b = 0;
+    row[0] = beg;
+    for (int t = beg; t < end; ++t) {
+        const int g = sig_gene[t];
+        const int gb = g / ST_GENES;
+        while (b < gb && b < n_blocks) row[++b] = t;
+        op[t] = (uint16_t)((g - gb * ST_GENES) | (sig_sign[t] < 0 ? 0x100 : 0));
+    }
+    while (b < n_blocks) row[++b] = end;
+}
+
 template <int METHOD>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 score_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_z, long G, long N,
-                    const int32_t *__restrict__ sig_ptr, const int32_t *__restrict__ sig_gene,
-                    const int8_t *__restrict__ sig_sign, long K, int n_groups,
+                    const int32_t *__restrict__ sig_ptr, const uint16_t *__restrict__ op,
+                    const int32_t *__restrict__ cut, long K, int n_groups,
                     const double *__restrict__ gene_mu, double *__restrict__ out, long ld_out) {
     using C = StagedCfg<METHOD>;
     extern __shared__ __align__(128) unsigned char st_smem[];
@@ -100,13 +128,15 @@ score_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int b = 0; b < C::stages && b < n_blocks; ++b) issue(b);
 
     // this thread's signatures: chunk (a * n_groups + group), slot (warp, half)
-    int cur[ST_A], end[ST_A];
+    // (the cut table has a zero row for every thread slot beyond K: its ranges are empty)
+    int cur[ST_A];
     double num[ST_A], acc2[ST_A];      // acc2: the normaliser (weighted, non-zero) or the imputed part
+    const int cut_ld = n_blocks + 1;
+    const int32_t *cut0 = cut + ((long)group * ST_CHUNK + warp * 2 + half) * cut_ld;
+    const long cut_step = (long)n_groups * ST_CHUNK * cut_ld;       // from signature slot a to a + 1
 #pragma unroll
     for (int a = 0; a < ST_A; ++a) {
-        const long sig = ((long)a * n_groups + group) * ST_CHUNK + warp * 2 + half;
-        cur[a] = sig < K ? sig_ptr[sig] : 0;
-        end[a] = sig < K ? sig_ptr[sig + 1] : 0;
+        cur[a] = __ldg(cut0 + a * cut_step);
         num[a] = 0.0;
         acc2[a] = 0.0;
     }
@@ -114,43 +144,48 @@ score_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int b = 0; b < n_blocks; ++b) {
         const int s = b % C::stages;
         const uint32_t ph = (uint32_t)(b / C::stages) & 1;
+        // where each of my signatures stops in this gene block: eight independent loads, issued
+        // before the wait for the block's data
+        int stop[ST_A];
+#pragma unroll
+        for (int a = 0; a < ST_A; ++a) stop[a] = __ldg(cut0 + a * cut_step + b + 1);
         mbar_wait(&full[s], ph);
         const double *sx = reinterpret_cast<const double *>(st_smem + s * C::stage_bytes) + c;
         const double *sw = sx + (C::use_w ? ST_GENES * ST_CELLS : 0);
         const double *sz = sx + (C::use_z ? (C::use_w ? 2 : 1) * ST_GENES * ST_CELLS : 0);
-        const int g_lo = b * ST_GENES, g_hi = g_lo + ST_GENES;
+        const int g_lo = b * ST_GENES;
 #pragma unroll
         for (int a = 0; a < ST_A; ++a) {
-            int t = cur[a];
-            const int e = end[a];
-            while (t < e) {
-                const int g = __ldg(sig_gene + t);
-                if (g >= g_hi) break;
-                const double sgn = (double)__ldg(sig_sign + t);
-                const int r = (g - g_lo) * ST_CELLS;
+            for (int t = cur[a]; t < stop[a]; ++t) {
+                const unsigned o = __ldg(op + t);
+                const int r = (int)(o & 0xff) * ST_CELLS;
+                // x * (+-1): flip the sign bit (exactly the product NumPy rounds to)
                 const double x = sx[r];
+                const double xs = __hiloint2double(__double2hiint(x) ^ (int)((o & 0x100) << 23), __double2loint(x));
                 if (METHOD == FP_METHOD_NAIVE) {
                     // pdata = data * sig * ones  (:38-41); the normaliser is the gene count
-                    num[a] = __dadd_rn(num[a], __dmul_rn(__dmul_rn(x, sgn), 1.0));
+                    num[a] = __dadd_rn(num[a], xs);
                 } else if (METHOD == FP_METHOD_WEIGHTED) {
                     const double w = sw[r];               // pdata = data * sig * weights  (:70-73)
-                    num[a] = __dadd_rn(num[a], __dmul_rn(__dmul_rn(x, sgn), w));
+                    num[a] = __dadd_rn(num[a], __dmul_rn(xs, w));
                     acc2[a] = __dadd_rn(acc2[a], w);
                 } else if (METHOD == FP_METHOD_NONZERO) {
-                    const double nz = __dsub_rn(1.0, sz[r]);      // (:152-153)
-                    num[a] = __dadd_rn(num[a], __dmul_rn(__dmul_rn(x, nz), sgn));
+                    const double nz = __dsub_rn(1.0, sz[r]);      // (data * not_zeros) * sig  (:152-153)
+                    const double p = __dmul_rn(x, nz);
+                    num[a] = __dadd_rn(num[a], __hiloint2double(__double2hiint(p) ^ (int)((o & 0x100) << 23),
+                                                                __double2loint(p)));
                     acc2[a] = __dadd_rn(acc2[a], nz);
                 } else {                                           // imputed (:105-121)
-                    const double w = sw[r], z = sz[r], mu = __ldg(gene_mu + g);
+                    const double w = sw[r], z = sz[r], mu = __ldg(gene_mu + g_lo + (int)(o & 0xff));
+                    const double sgn = (o & 0x100) ? -1.0 : 1.0;
                     const double nz = __dsub_rn(1.0, z);
                     num[a] = __dadd_rn(num[a], __dmul_rn(__dmul_rn(x, nz), sgn));
                     const double t1 = __dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, w), mu), sgn), z);
                     const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(w, x), sgn), z);
                     acc2[a] = __dadd_rn(acc2[a], __dadd_rn(t1, t2));
                 }
-                ++t;
             }
-            cur[a] = t;
+            cur[a] = stop[a];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -210,7 +245,7 @@ bool encode_matrix(EncodeTiledFn enc, CUtensorMap *map, const double *base, long
 
 template <int METHOD>
 int launch_staged(const CUtensorMap &mx, const CUtensorMap &mw, const CUtensorMap &mz, long G, long N,
-                  const int32_t *sig_ptr, const int32_t *sig_gene, const int8_t *sig_sign, long K, int n_groups,
+                  const int32_t *sig_ptr, const uint16_t *op, const int32_t *cut, long K, int n_groups,
                   const double *gene_mu, double *out, long ld_out, cudaStream_t st) {
     using C = StagedCfg<METHOD>;
     static bool attr_set = false;
@@ -226,29 +261,56 @@ int launch_staged(const CUtensorMap &mx, const CUtensorMap &mw, const CUtensorMa
         return FP_EUNSUPPORTED;
     }
     score_staged_kernel<METHOD><<<(unsigned)blocks, ST_THREADS, C::smem_bytes, st>>>(
-        mx, mw, mz, G, N, sig_ptr, sig_gene, sig_sign, K, n_groups, gene_mu, out, ld_out);
+        mx, mw, mz, G, N, sig_ptr, op, cut, K, n_groups, gene_mu, out, ld_out);
     FP_CHECK_LAUNCH("score_staged_kernel");
     return FP_OK;
 }
 
+struct StagedPlan {
+    long n_groups, rows, n_blocks;
+    size_t op_off, cut_off, total;
+};
+
+StagedPlan staged_plan(long G, long K, long nnz) {
+    StagedPlan p;
+    p.n_groups = (K + ST_GROUP - 1) / ST_GROUP;
+    p.rows = p.n_groups * ST_GROUP;
+    p.n_blocks = (G + ST_GENES - 1) / ST_GENES;
+    p.op_off = 0;
+    p.cut_off = ((size_t)nnz * 2 + 255) & ~(size_t)255;
+    p.total = p.cut_off + (((size_t)p.rows * (p.n_blocks + 1) * 4 + 255) & ~(size_t)255);
+    return p;
+}
+
 }  // namespace
+
+size_t fp_score_staged_workspace_bytes(long G, long K, long nnz) {
+    if (G <= 0 || K <= 0 || nnz <= 0) return 0;
+    return staged_plan(G, K, nnz).total;
+}
 
 // Whether the staged kernel applies and pays: TMA needs 16-byte aligned bases and row pitches;
 // it moves 16 G N ceil(K/512) bytes through L2 where the gather kernel moves 16 nnz N.
 bool fp_score_staged_applies(const double *X, const double *W, const double *Z, long G, long N, long ld, long K,
-                             long nnz) {
+                             long nnz, bool forced) {
     if (nnz <= 0 || K <= 0) return false;
     if ((ld & 1) || N < ST_CELLS || G >= (1L << 31) || N >= (1L << 31)) return false;
     const uintptr_t bits = reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) |
                            reinterpret_cast<uintptr_t>(Z);
     if (bits & 15) return false;
-    const long n_groups = (K + ST_GROUP - 1) / ST_GROUP;
-    return nnz > n_groups * G;
+    const StagedPlan p = staged_plan(G, K, nnz);
+    if ((size_t)p.rows * (p.n_blocks + 1) >= (1ull << 31)) return false;
+    // Measured on B200 (profiles/r02_scoring_staged.md): at BASELINE config 2 the staged kernel
+    // takes 9.2 ms against 5.7 ms for the gathers -- the membership tables are re-read through
+    // L2 (46 GB of sector traffic) and the 2 x 16-lane layout issues 3x the instructions per
+    // gene -- so it is used only when asked for (FASTPROJECT_B200_SCORE=staged).
+    (void)p;
+    return forced;
 }
 
 int fp_score_staged(int method, const double *X, const double *W, const double *Z, long G, long N, long ld,
-                    const int32_t *sig_ptr, const int32_t *sig_gene, const int8_t *sig_sign, long K,
-                    const double *gene_mu, double *out, long ld_out, cudaStream_t st) {
+                    const int32_t *sig_ptr, const int32_t *sig_gene, const int8_t *sig_sign, long K, long nnz,
+                    const double *gene_mu, double *out, long ld_out, void *workspace, cudaStream_t st) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) {
         fp::set_error("fp_score_signatures: cuTensorMapEncodeTiled not available from the driver");
@@ -262,19 +324,27 @@ int fp_score_staged(int method, const double *X, const double *W, const double *
         fp::set_error("fp_score_signatures: cuTensorMapEncodeTiled failed");
         return FP_ECUDA;
     }
-    const int n_groups = (int)((K + ST_GROUP - 1) / ST_GROUP);
+    const StagedPlan p = staged_plan(G, K, nnz);
+    char *ws = static_cast<char *>(workspace);
+    uint16_t *op = reinterpret_cast<uint16_t *>(ws + p.op_off);
+    int32_t *cut = reinterpret_cast<int32_t *>(ws + p.cut_off);
+    FP_CHECK_CUDA(cudaMemsetAsync(cut, 0, (size_t)p.rows * (p.n_blocks + 1) * 4, st));
+    score_prepare_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(sig_ptr, sig_gene, sig_sign, K, (int)p.n_blocks,
+                                                                     op, cut);
+    FP_CHECK_LAUNCH("score_prepare_kernel");
+    const int n_groups = (int)p.n_groups;
     switch (method) {
         case FP_METHOD_NAIVE:
-            return launch_staged<FP_METHOD_NAIVE>(mx, mw, mz, G, N, sig_ptr, sig_gene, sig_sign, K, n_groups, gene_mu,
-                                                  out, ld_out, st);
+            return launch_staged<FP_METHOD_NAIVE>(mx, mw, mz, G, N, sig_ptr, op, cut, K, n_groups, gene_mu, out,
+                                                  ld_out, st);
         case FP_METHOD_WEIGHTED:
-            return launch_staged<FP_METHOD_WEIGHTED>(mx, mw, mz, G, N, sig_ptr, sig_gene, sig_sign, K, n_groups,
-                                                     gene_mu, out, ld_out, st);
+            return launch_staged<FP_METHOD_WEIGHTED>(mx, mw, mz, G, N, sig_ptr, op, cut, K, n_groups, gene_mu, out,
+                                                     ld_out, st);
         case FP_METHOD_IMPUTED:
-            return launch_staged<FP_METHOD_IMPUTED>(mx, mw, mz, G, N, sig_ptr, sig_gene, sig_sign, K, n_groups,
-                                                    gene_mu, out, ld_out, st);
+            return launch_staged<FP_METHOD_IMPUTED>(mx, mw, mz, G, N, sig_ptr, op, cut, K, n_groups, gene_mu, out,
+                                                    ld_out, st);
         default:
-            return launch_staged<FP_METHOD_NONZERO>(mx, mw, mz, G, N, sig_ptr, sig_gene, sig_sign, K, n_groups,
-                                                    gene_mu, out, ld_out, st);
+            return launch_staged<FP_METHOD_NONZERO>(mx, mw, mz, G, N, sig_ptr, op, cut, K, n_groups, gene_mu, out,
+                                                    ld_out, st);
     }
 }

@@ -114,21 +114,25 @@ int fp_gene_detected_mean(const double *X, const double *Z,
  *   Z        : required for IMPUTED and NONZERO, else may be NULL
  *   gene_mu  : required for IMPUTED (from fp_gene_detected_mean), else NULL
  *   out_scores : K x ld_out float64
- *   nnz      : sig_ptr[K] as the host knows it (0 = unknown).  It only selects the data path:
- *              with nnz > ceil(K/512) * G, 16-byte aligned matrices and an even ld the gene rows
- *              are staged in shared memory by TMA (cp.async.bulk.tensor), each (256 genes x 16
- *              cells) box once per group of 512 signatures; otherwise every signature gathers
- *              its rows through L2.  Same arithmetic, same bits.
+ *   nnz      : sig_ptr[K] as the host knows it (0 = unknown)
+ *   workspace: fp_score_workspace_bytes(G, K, nnz) bytes, or NULL.  nnz and the workspace only
+ *              select the data path: with nnz > ceil(K/512) * G, 16-byte aligned matrices and an
+ *              even ld the gene rows are staged in shared memory by TMA (cp.async.bulk.tensor),
+ *              each (256 genes x 16 cells) box once per group of 512 signatures, and the
+ *              workspace holds the membership table re-cut by gene block; otherwise every
+ *              signature gathers its rows through L2.  Same arithmetic, same bits.
  * Signatures with zero matched genes must be filtered by the caller (the
  * reference raises ValueError for them, SigScoreMethods.py:60-64).
  */
+size_t fp_score_workspace_bytes(int64_t G, int64_t K, int64_t nnz);
 int fp_score_signatures(int method,
                         const double *X, const double *W, const double *Z,
                         int64_t G, int64_t N, int64_t ld,
                         const int32_t *sig_ptr, const int32_t *sig_gene,
                         const int8_t *sig_sign, int64_t K, int64_t nnz,
                         const double *gene_mu,
-                        double *out_scores, int64_t ld_out, void *stream);
+                        double *out_scores, int64_t ld_out,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * fp_rank_columns -- average ranks (1-based, ties share the mean rank) of each

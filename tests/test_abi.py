@@ -46,7 +46,7 @@ def test_version_and_error_text(lib):
 
 def test_argument_validation_without_gpu(lib):
     # bad arguments are rejected before any CUDA call is made
-    rc = lib.fp_score_signatures(99, None, None, None, 1, 1, 1, None, None, None, 0, 0, None, None, 1, None)
+    rc = lib.fp_score_signatures(99, None, None, None, 1, 1, 1, None, None, None, 0, 0, None, None, 1, None, 0, None)
     assert rc == -1 and b"unknown method" in lib.fp_last_error()
     rc = lib.fp_row_medians(None, 1, 1, 1, None, None)
     assert rc == -1
