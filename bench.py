@@ -82,6 +82,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 block")
     ap.add_argument("--c3-steps", type=int, default=3)
+    ap.add_argument("--no-c5", action="store_true", help="skip the scoring-only sweep")
     return ap.parse_args()
 
 
@@ -558,11 +559,68 @@ def run_b200(args):
         c3 = run_block("C3", args, device, world, rank, args.c3_steps, 1)
         if rank == 0:
             result["c3"] = c3
+    # BASELINE configs[4]: signature-scoring-only sweep (cell x signature scores/s against the HBM roofline)
+    if not args.no_c5 and args.workload == "C2" and world == 1:
+        E.clear_device_cache()
+        torch.cuda.empty_cache()
+        result["c5"] = run_scoring_sweep(device)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         emit(result)
+
+
+C5_SHAPES = [  # genes, cells, signatures
+    (15000, 10000, 1000), (15000, 10000, 10000), (15000, 100000, 1000), (15000, 100000, 10000),
+    (15000, 100000, 50000), (2000, 1000000, 1000), (2000, 1000000, 10000),
+]
+
+
+def run_scoring_sweep(device):
+    """fp_score_signatures alone (weighted_avg, random signatures of the reference's six sizes) on
+    resident matrices: time per launch (CUDA events, best of 2 after a warm-up; the matrices are
+    larger than L2), scores/s, and the fraction of the HBM roofline on the compulsory bytes
+    16 G N + 8 N K + 5 nnz."""
+    import gc
+    import random
+    import numpy as np
+    import torch
+    from fastproject_b200 import Signatures as S, _engine as E, _scoring
+    peaks = measured_peaks()
+    rows = []
+    for G, N, K in C5_SHAPES:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(G + N)
+        x = torch.randn((G, N), dtype=torch.float64, device=device, generator=gen)
+        w = torch.rand((G, N), dtype=torch.float64, device=device, generator=gen)
+        genes = ["G%05d" % i for i in range(G)]
+        random.seed(1)
+        np.random.seed(1)
+        sigs = S.generate_random_sigs(genes, False, SIZES, (K + 5) // 6)[:K]
+        kept, sp, sg, ss, _ = _scoring.pack_signatures(sigs, genes, 5)
+        dp, dg, ds = E.to_device(sp, torch.int32), E.to_device(sg, torch.int32), E.to_device(ss, torch.int8)
+        E.score_signatures("weighted_avg", x, w, None, dp, dg, ds, len(kept))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for r in range(2):
+            E.score_signatures("weighted_avg", x, w, None, dp, dg, ds, len(kept))
+            ev[r + 1].record()
+        torch.cuda.synchronize()
+        ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(2))
+        nnz = int(sp[-1])
+        compulsory = G * N * 16.0 + N * len(kept) * 8.0 + 5.0 * nnz
+        rows.append({"genes": G, "cells": N, "signatures": len(kept), "nnz": nnz, "ms": ms,
+                     "scores_per_sec": N * len(kept) / (ms * 1e-3),
+                     "compulsory_GBps": compulsory / ms / 1e6,
+                     "frac_of_hbm_roofline": compulsory / ms / 1e6 / peaks["hbm_gbs"],
+                     "gather_GBps": 16.0 * nnz * N / ms / 1e6})
+        del x, w, dp, dg, ds
+        gc.collect()
+        torch.cuda.empty_cache()
+    return {"kernel": "fp_score_signatures (weighted_avg, gather kernel)", "peak_GBps": peaks["hbm_gbs"],
+            "note": "gather_GBps = 16 nnz N / t is the L2 -> SM rate of the gathers (cap of the part: ~12 TB/s)",
+            "rows": rows}
 
 
 def run_block(name, args, device, world, rank, steps, warmup):
@@ -606,18 +664,21 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     G, N, P = cfg["G"], cfg["N"], cfg["P"]
     # two pinned host buffers: consecutive steps are different host arrays, so every step uploads
     # its own input; the upload of step k+1 is started at the beginning of step k
+    from fastproject_b200 import distributed as D
+    dist_mode = world > 1
+    rank = dist.get_rank() if dist_mode else 0
+    row_lo, row_hi = D.shard_bounds(G, world, rank)
     host = []
     for _ in range(2):
-        rh = torch.empty((G, N), dtype=torch.float64, pin_memory=True)
-        rh.copy_(wl["raw"])
+        # every rank holds (and uploads) only its block of gene rows of the job's matrix
+        rh = torch.empty((row_hi - row_lo, N), dtype=torch.float64, pin_memory=True)
+        rh.copy_(wl["raw"][row_lo:row_hi])
         host.append(rh.numpy())
     wl["raw"] = None
     params = wl["params"]
     torch.cuda.synchronize()
     steps = max(args.steps, 12)
     warm = max(args.warmup, 3)
-    dist_mode = world > 1
-
     trace = [] if os.environ.get("FP_BENCH_DEBUG") else None
 
     def stamp(what):
@@ -626,12 +687,17 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
 
     def one_step(raw, nxt):
         stamp("begin")
-        FP.prefetch(raw, replicated=dist_mode)
+        FP.prefetch(raw)
         if nxt is not None:
-            FP.prefetch(nxt, replicated=dist_mode)
-        raw_dev = E.expression_cache.get(raw, dist_mode)
+            FP.prefetch(nxt)
+        raw_dev = E.expression_cache.get(raw)
+        # weights and z-scores are per-gene-row operations: each rank makes them for its rows
         w_dev = T.compute_weights(None, params, raw_dev)                       # Pipelines.py:120
         x_dev = NM.row_normalization(raw_dev)                                  # Pipelines.py:202
+        if dist_mode:                                                          # all rows to every GPU over NVLink
+            bounds = D.even_bounds(G, world)
+            w_dev = D.all_gather_row_blocks(w_dev, bounds)
+            x_dev = D.all_gather_row_blocks(x_dev, bounds)
         data = synth.ExpressionMatrix(x_dev, w_dev, wl["genes"], wl["cells"])
         stamp("prep issued")
         real = S.calculate_sig_scores(data, wl["real"], "weighted_avg", None, 5, distributed=dist_mode)
@@ -675,7 +741,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     t = dt / steps
     n_rows = len(real) + len(rnd)
     nnz = sum(len(s.sig_dict) for s in wl["real"]) + sum(len(s.sig_dict) for s in wl["rnd"])
-    # the raw matrix is one data set: every rank uploads 1/world of its rows (all-gathered over NVLink)
+    # the raw matrix is one data set: every rank uploads its 1/world of the gene rows
     h2d = G * N * 8 + nnz * 5 + (n_rows + world) * 4 + world * (P * 2 * N * 8 + 4 * N * 8)
     return {"value": n_rows * P / t, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "s_per_step": t, "steps": steps,
@@ -683,8 +749,9 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
                    "row_normalization on the device -> Signatures.calculate_sig_scores x2 -> Signatures."
                    "sigs_vs_projections(distributed=%s); pinned host input; steps back to back, the upload of "
                    "the next step's matrix overlaps the current step%s"
-                   % (dist_mode, "; one job: every rank uploads 1/world of the rows over its PCIe link and the "
-                      "rows are all-gathered over NVLink" if dist_mode else "")}
+                   % (dist_mode, "; one job: every rank uploads its 1/world of the gene rows over its own PCIe "
+                      "link, makes weights and z-scores for them, and X / W are all-gathered over NVLink"
+                      if dist_mode else "")}
 
 
 # ----------------------------------------------------------------------------

@@ -620,6 +620,10 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             // both CTAs' bytes of a stage are counted on the leader's barrier: the leader cannot run
             // ahead of a peer that has not issued its loads, so neither producer is ever lapped
             constexpr uint32_t tx_bytes = 2 * L::stage_bytes;
+            // (Round 2 tried an L2 evict_last hint on the value planes, which every cell tile
+            // re-reads: the 140 MB of planes then pushed the weight planes out before their 14
+            // readers were through -- 13.1 GB of DRAM reads per launch instead of 9.5, same time:
+            // the kernel is bound by the tensor pipe.  Plain loads stay.)
             long g = 0;                                       // stages issued by this CTA so far
             for (int item = pair; item < n_items; item += n_pairs) {
                 const long tile_row = (long)(item / n_sig_pairs) * TN;       // slab-relative first cell

@@ -39,12 +39,20 @@ constexpr int kSigsPerBlock = 16;     // blockDim.y
 constexpr int kDepth = 8;             // genes in flight per thread
 constexpr int kMinBlocks = 2;         // CTAs per SM the register budget is set for (64 registers)
 
-__device__ __forceinline__ double ldg_stream(const double *p) {
-    // read-only, keep out of L1 (each value is used once by this thread); not volatile, so
-    // the compiler may hoist the loads of later genes above the arithmetic of earlier ones
+__device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy) {
+    // read-only, keep out of L1 (each value is used once by this thread) but LAST to leave L2:
+    // the same gene row is gathered by ~nnz/G other signatures of this 32-cell slab within
+    // microseconds (ncu, round 2: without the hint the slab was re-fetched from HBM 3.7 times,
+    // 17.7 GB of DRAM reads for 4.8 GB of input).  Not volatile, so the compiler may hoist the
+    // loads of later genes above the arithmetic of earlier ones.
     double v;
-    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
     return v;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t policy;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
 }
 
 // one gene's contribution, the reference's operation order
@@ -85,6 +93,7 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
     constexpr bool kUseMu = METHOD == FP_METHOD_IMPUTED;
     // the imputed method carries three operands + mu per gene: half the depth keeps it in registers
     constexpr int D = METHOD == FP_METHOD_IMPUTED ? kDepth / 2 : kDepth;
+    const uint64_t keep = l2_evict_last_policy();
     for (long slab = blockIdx.y; slab * kCellsPerBlock < N; slab += gridDim.y) {
     const long cell = slab * kCellsPerBlock + threadIdx.x;
     const bool live = cell < N;
@@ -102,9 +111,9 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
 #pragma unroll
             for (int e = 0; e < D; ++e) {
                 const long o = (long)g[e] * ld + c;
-                x[e] = ldg_stream(X + o);
-                w[e] = kUseW ? ldg_stream(W + o) : 0.0;
-                z[e] = kUseZ ? ldg_stream(Z + o) : 0.0;
+                x[e] = ldg_stream(X + o, keep);
+                w[e] = kUseW ? ldg_stream(W + o, keep) : 0.0;
+                z[e] = kUseZ ? ldg_stream(Z + o, keep) : 0.0;
             }
 #pragma unroll
             for (int e = 0; e < D; ++e) {
@@ -117,9 +126,9 @@ score_gather_kernel(const double *__restrict__ X, const double *__restrict__ W,
         for (; t < end; ++t) {
             const int g = sig_gene[t];
             const long o = (long)g * ld + c;
-            const double x = ldg_stream(X + o);
-            const double w = kUseW ? ldg_stream(W + o) : 0.0;
-            const double z = kUseZ ? ldg_stream(Z + o) : 0.0;
+            const double x = ldg_stream(X + o, keep);
+            const double w = kUseW ? ldg_stream(W + o, keep) : 0.0;
+            const double z = kUseZ ? ldg_stream(Z + o, keep) : 0.0;
             accumulate<METHOD>(x, w, z, kUseMu ? gene_mu[g] : 0.0, (double)sig_sign[t], num, den, aux);
         }
         double score;

@@ -193,6 +193,20 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         "l"(map), "r"(c0), "r"(c1), "r"(leader_bar_addr)
         : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy) for operands that many CTAs re-read
+__device__ __forceinline__ void tma_load_2d_pair_hint(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                                      uint32_t leader_bar_addr, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar_addr), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
 // executed by one full warp in EACH CTA of the pair, same destination offset
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
