@@ -264,7 +264,8 @@ class ResidentJob(object):
         self.d_grp = E.to_device(grp, torch.int32)
         self.ld = E.padded(N)
         widest = max([h - l for _, l, h in self.runs] or [1])
-        self.dissim = torch.empty((widest, self.ld), dtype=torch.float64, device=device)
+        self.overlap = E.MedianOverlap(widest, self.ld, device)
+        self.dissim = self.overlap.bufs[0]
         self.med_all = torch.zeros((P, self.n_rows), dtype=torch.float64, device=device)
         self.p_all = torch.empty((P, self.n_real), dtype=torch.float64, device=device)
         self.sig2 = SIGMA ** 2
@@ -295,11 +296,13 @@ class ResidentJob(object):
             self.med_all.zero_()
         mark("gather")
         for p, lo, hi in self.runs:
-            dis = E.consistency(self.coords[p], self.sig2, ranks[lo:hi], N, out=self.dissim[:hi - lo],
+            # the median of this run goes to a side stream and overlaps the next run's weight planes
+            dis = E.consistency(self.coords[p], self.sig2, ranks[lo:hi], N, out=self.overlap.buffer(hi - lo),
                                 precision=self.precision, slot="bench")
             mark("consistency")
-            self.med_all[p, lo:hi] = E.row_medians(dis, N)
-            mark("median")
+            self.overlap.median_into(dis, N, self.med_all[p, lo:hi])
+        self.overlap.join()
+        mark("median (last one; the others overlap the next contraction)")
         if self.world > 1:
             D.all_reduce_sum(self.med_all)
         for i in range(P):

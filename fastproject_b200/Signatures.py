@@ -303,9 +303,8 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
         my_runs = [(i, 0, n_rows) for i in range(N_PROJECTIONS)] if n_rows else []
     med_all = torch.zeros((N_PROJECTIONS, n_rows), dtype=torch.float64, device=dev)
     if my_runs:
-        dissim = torch.empty((max(hi - lo for _, lo, hi in my_runs), ranks.shape[1]),
-                             dtype=torch.float64, device=dev)
-        _contract_runs(my_runs, coords_all, sig2, ranks, N_SAMPLES, dissim, med_all, precision)
+        overlap = _engine.MedianOverlap(max(hi - lo for _, lo, hi in my_runs), ranks.shape[1], dev)
+        _contract_runs(my_runs, coords_all, sig2, ranks, N_SAMPLES, overlap, med_all, precision)
     if world_size > 1:
         D.all_reduce_sum(med_all)                                       # the one exchange of stage 2
     p_all = torch.empty((N_PROJECTIONS, N_SIGNATURES), dtype=torch.float64, device=dev)
@@ -358,13 +357,14 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             random_sig_proj_matrix, random_sig_score_keys)
 
 
-def _contract_runs(runs, coords_all, sig2, ranks, n, dissim, med_all, precision):
+def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision):
     """med_all[p, lo:hi] = median over cells of |rank - neighbourhood prediction| for every
-    run (projection p, rows lo..hi) -- :396-414.  The tensor-core mode refuses values it
-    cannot represent exactly; "auto" then repeats the run on the FP64 kernel, "tc" raises."""
+    run (projection p, rows lo..hi) -- :396-414.  The median of one run is taken on a side stream
+    while the next run's weight planes are generated (``_engine.MedianOverlap``).  The tensor-core
+    mode refuses values it cannot represent exactly; "auto" then repeats the run on the FP64
+    kernel, "tc" raises."""
     requested = precision or _engine.default_precision()
     pending = None                      # (rows view, indices of the runs launched on that shape)
-    todo = list(range(len(runs)))
 
     def settle(batch):
         view, idxs = batch
@@ -374,24 +374,25 @@ def _contract_runs(runs, coords_all, sig2, ranks, n, dissim, med_all, precision)
                     "sigs_vs_projections(precision=%r): the values are not exactly representable on the "
                     "tensor-core path (NaN / inf ranks, non-half-integers or too wide a range); use "
                     "precision='fp64' or 'auto'" % (requested,))
+            overlap.join()              # the refused runs' (NaN) medians must land before their replacement
             for r in idxs:
                 p, lo, hi = runs[r]
-                dis = _engine.consistency(coords_all[p], sig2, ranks[lo:hi], n, out=dissim[:hi - lo],
+                dis = _engine.consistency(coords_all[p], sig2, ranks[lo:hi], n, out=overlap.buffer(hi - lo),
                                           precision="fp64", slot="svp")
-                med_all[p, lo:hi] = _engine.row_medians(dis, n)
+                overlap.median_into(dis, n, med_all[p, lo:hi])
 
-    for r in todo:
-        p, lo, hi = runs[r]
+    for r, (p, lo, hi) in enumerate(runs):
         view = ranks[lo:hi]
         if pending is not None and pending[0].shape[0] != view.shape[0]:
             settle(pending)             # the flag lives in a workspace laid out for that shape
             pending = None
-        dis = _engine.consistency(coords_all[p], sig2, view, n, out=dissim[:hi - lo],
+        dis = _engine.consistency(coords_all[p], sig2, view, n, out=overlap.buffer(hi - lo),
                                   precision=requested, slot="svp")
-        med_all[p, lo:hi] = _engine.row_medians(dis, n)
+        overlap.median_into(dis, n, med_all[p, lo:hi])
         pending = (view, (pending[1] if pending else []) + [r])
     if pending is not None:
         settle(pending)
+    overlap.join()
 
 
 def _single_group_pvalue(med_value, bg_medians):

@@ -500,6 +500,50 @@ def row_medians(values, n):
     return out
 
 
+_median_stream = None
+
+
+class MedianOverlap(object):
+    """Runs ``fp_row_medians`` of one projection on a side stream while the main stream already
+    generates the weight planes of the next one (the median kernel is a bandwidth-bound sweep,
+    the weight planes are FP64-bound: they share the SMs well).  Two dissimilarity buffers
+    alternate; a buffer is handed back to the contraction only after the median that read it.
+    Same kernels, same arguments, same results -- only the stream differs."""
+
+    def __init__(self, rows, ld, device):
+        global _median_stream
+        if _median_stream is None:
+            _median_stream = torch.cuda.Stream(device=device)
+        self.side = _median_stream
+        self.bufs = [torch.empty((rows, ld), dtype=torch.float64, device=device) for _ in range(2)]
+        self.done = [None, None]
+        self.turn = 0
+
+    def buffer(self, rows):
+        """The dissimilarity buffer for the next contraction (main stream)."""
+        k = self.turn & 1
+        if self.done[k] is not None:
+            torch.cuda.current_stream().wait_event(self.done[k])
+        return self.bufs[k][:rows]
+
+    def median_into(self, dis, n, dest):
+        """dest[...] = row medians of ``dis`` (just written by the main stream), on the side stream."""
+        k = self.turn & 1
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            dest.copy_(row_medians(dis, n))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[k] = ev
+        self.turn += 1
+
+    def join(self):
+        """Main stream waits for every median issued so far."""
+        torch.cuda.current_stream().wait_stream(self.side)
+
+
 def background_pvalues(med, sig_group, rnd_med, rnd_order, group_ptr):
     """All arguments CUDA tensors (float64 / int32).  Returns (p, mu, sigma)."""
     k = med.shape[0]
