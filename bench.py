@@ -242,15 +242,19 @@ class ResidentJob(object):
         self.n_rows = len(kept)
         self.counts = counts
         self.nnz = int(sig_ptr[-1])
-        # stage 1: my rows of the signature batch
-        self.bounds = D.even_bounds(self.n_rows, world)
-        lo, hi = self.bounds[rank]
-        self.rows = (lo, hi)
-        e0, e1 = int(sig_ptr[lo]), int(sig_ptr[hi])
-        self.nnz_local = e1 - e0
-        self.d_ptr = E.to_device((sig_ptr[lo:hi + 1] - sig_ptr[lo]).astype(np.int32), torch.int32)
-        self.d_gene = E.to_device(sig_gene[e0:e1], torch.int32)
-        self.d_sign = E.to_device(sig_sign[e0:e1], torch.int8)
+        # stage 1: my rows of the signature batch, dealt round-robin (same mix of sizes on every rank)
+        self.owner_rows = D.cyclic_owner_rows(self.n_rows, world)
+        mine = self.owner_rows[rank]
+        self.rows = mine
+        starts, stops = sig_ptr[mine].astype(np.int64), sig_ptr[mine + 1].astype(np.int64)
+        lens = stops - starts
+        local_ptr = np.zeros(mine.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=local_ptr[1:])
+        take = np.concatenate([np.arange(a, b) for a, b in zip(starts, stops)]) if mine.size else np.zeros(0, np.int64)
+        self.nnz_local = int(local_ptr[-1])
+        self.d_ptr = E.to_device(local_ptr.astype(np.int32), torch.int32)
+        self.d_gene = E.to_device(sig_gene[take], torch.int32)
+        self.d_sign = E.to_device(sig_sign[take], torch.int8)
         # stage 2: my runs of the (projection x signature-block) grid
         self.proj_names = sorted(wl["projections"].keys())
         self.coords = E.to_device(np.stack([wl["projections"][p] for p in self.proj_names]))
@@ -287,12 +291,12 @@ class ResidentJob(object):
 
         mark("begin")
         scores = E.score_signatures("weighted_avg", self.wl["x"], self.wl["w"], None, self.d_ptr, self.d_gene,
-                                    self.d_sign, self.rows[1] - self.rows[0])
+                                    self.d_sign, int(self.rows.size))
         mark("score")
         ranks = E.rank_rows(scores, N)
         mark("rank")
         if self.world > 1:
-            ranks = D.all_gather_row_blocks(ranks, self.bounds)
+            ranks = D.all_gather_owned_rows(ranks, self.owner_rows)
             self.med_all.zero_()
         mark("gather")
         for p, lo, hi in self.runs:
@@ -396,7 +400,7 @@ def rooflines(job, ms_step, workload):
                 algorithmic="2*N^2 flop per (signature, projection) pair; one launch = one projection x "
                             "(this rank's rows + 1 normaliser row)")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    rows_local = job.rows[1] - job.rows[0]
+    rows_local = int(job.rows.size)
     score_ms = st.get("score", 0.0)
     score_bytes = G * N * 16.0 + N * rows_local * 8.0 + 5.0 * job.nnz_local
     s_traffic, s_src = captured_traffic(workload, job.precision, "fp_score_signatures")
@@ -446,28 +450,33 @@ def subset_parity(job, n_sigs=16, n_cells=1024):
         return None
     p, lo, hi = job.runs[0]
     N = job.cfg["N"]
-    take = min(n_sigs, hi - lo, job.rows[1] - job.rows[0])
+    # rank 0's first signatures (its rows are every world-th row of the job) inside its first run
+    rows = job.rows[:n_sigs]
+    rows = rows[(rows >= lo) & (rows < hi)]
+    take = int(rows.size)
     sigs = (job.wl["real"] + job.wl["rnd"])
     from fastproject_b200 import _scoring
     kept, _, _, _, _ = _scoring.pack_signatures(sigs, job.wl["genes"], 5)
-    chosen = [sigs[kept[r]] for r in range(lo, lo + take)]
+    chosen = [sigs[kept[r]] for r in rows]
     gene_pos = dict((g, i) for i, g in enumerate(job.wl["genes"]))
-    rows = sorted(set(gene_pos[g] for s in chosen for g in s.sig_dict if g in gene_pos))
-    idx = torch.tensor(rows, dtype=torch.long, device=job.device)
+    grows = sorted(set(gene_pos[g] for s in chosen for g in s.sig_dict if g in gene_pos))
+    idx = torch.tensor(grows, dtype=torch.long, device=job.device)
     xs = job.wl["x"].index_select(0, idx).cpu().numpy()
     ws = job.wl["w"].index_select(0, idx).cpu().numpy()
-    odata = O.ExpressionMatrix(xs, ws, [job.wl["genes"][r] for r in rows], job.wl["cells"])
+    odata = O.ExpressionMatrix(xs, ws, [job.wl["genes"][r] for r in grows], job.wl["cells"])
     ores = O.calculate_sig_scores(odata, [O.Signature(s.sig_dict, s.signed, s.source, s.name) for s in chosen],
                                   "weighted_avg", None, 5)
     want_scores = np.array([ores[s.name].scores for s in chosen])
     want_ranks = np.array([ores[s.name].ranks for s in chosen])
-    # GPU: scores / ranks of those rows (rank 0's rows start at 0 = lo) and the contraction
+    # GPU: scores of those rows (the first of rank 0's local rows), their ranks in the gathered
+    # matrix, and the contraction of the run they belong to
+    rows_dev = torch.from_numpy(rows).to(job.device)
     got_scores = job.last_scores[:take, :N].cpu().numpy()
-    got_ranks = job.last_ranks[lo:lo + take, :N].cpu().numpy()
+    got_ranks = job.last_ranks.index_select(0, rows_dev)[:, :N].cpu().numpy()
     dis = job.E.consistency(job.coords[p], job.sig2, job.last_ranks[lo:hi], N, out=job.dissim[:hi - lo],
                             precision=job.precision, slot="bench")
     cells = np.sort(np.random.RandomState(11).choice(N, size=min(n_cells, N), replace=False))
-    got = dis[:take].index_select(1, torch.from_numpy(cells).to(job.device)).cpu().numpy()
+    got = dis.index_select(0, rows_dev - lo).index_select(1, torch.from_numpy(cells).to(job.device)).cpu().numpy()
     coords = job.wl["projections"][job.proj_names[p]]
     want = np.empty_like(got)
     vt = np.ascontiguousarray(want_ranks.T)

@@ -176,16 +176,16 @@ class ScoreBatch(object):
     """Scores of many signatures on the same cells, resident on the device as a
     [signatures x ld] float64 matrix (one signature per row).
 
-    In a multi-GPU job (``bounds`` given) this rank holds only the rows
-    ``bounds[rank] = [lo, hi)`` of the job's batch; ``ranks_dev`` / ``host_scores`` /
-    ``host_ranks`` return ALL rows and contain one all-gather over NVLink the first time they
-    are used -- every rank must reach them in the same order (``sigs_vs_projections`` does)."""
+    In a multi-GPU job (``owner_rows`` given) this rank holds only the rows
+    ``owner_rows[rank]`` of the job's batch; ``ranks_dev`` / ``host_scores`` / ``host_ranks``
+    return ALL rows in job order and contain one all-gather over NVLink the first time they are
+    used -- every rank must reach them in the same order (``sigs_vs_projections`` does)."""
 
-    def __init__(self, scores_dev, n_cells, num_genes, bounds=None, rank=0):
+    def __init__(self, scores_dev, n_cells, num_genes, owner_rows=None, rank=0):
         self.scores_dev = scores_dev          # local rows
         self.n_cells = int(n_cells)
         self.num_genes = num_genes            # all rows of the job
-        self.bounds = bounds
+        self.owner_rows = owner_rows
         self.rank = rank
         self._ranks_dev = None
         self._host_scores = None
@@ -193,11 +193,16 @@ class ScoreBatch(object):
 
     @property
     def n_rows(self):
-        return self.bounds[-1][1] if self.bounds is not None else self.scores_dev.shape[0]
+        if self.owner_rows is not None:
+            return sum(len(r) for r in self.owner_rows)
+        return self.scores_dev.shape[0]
 
     @property
     def local_rows(self):
-        return self.bounds[self.rank] if self.bounds is not None else (0, self.scores_dev.shape[0])
+        """Job rows held by this rank (ascending)."""
+        if self.owner_rows is not None:
+            return self.owner_rows[self.rank]
+        return np.arange(self.scores_dev.shape[0], dtype=np.int64)
 
     def local_ranks_dev(self):
         return _engine.rank_rows(self.scores_dev, self.n_cells)
@@ -205,22 +210,22 @@ class ScoreBatch(object):
     def ranks_dev(self):
         if self._ranks_dev is None:
             local = self.local_ranks_dev()
-            if self.bounds is not None:
+            if self.owner_rows is not None:
                 from . import distributed as D
-                local = D.all_gather_row_blocks(local, self.bounds)
+                local = D.all_gather_owned_rows(local, self.owner_rows)
             self._ranks_dev = local
         return self._ranks_dev
 
     def host_scores_local(self):
-        """This rank's rows only (no collective)."""
+        """This rank's rows only (no collective), in the order of ``local_rows``."""
         return _engine.to_host(self.scores_dev[:, :self.n_cells])
 
     def host_scores(self):
         if self._host_scores is None:
             dev = self.scores_dev
-            if self.bounds is not None:
+            if self.owner_rows is not None:
                 from . import distributed as D
-                dev = D.all_gather_row_blocks(dev, self.bounds)
+                dev = D.all_gather_owned_rows(dev, self.owner_rows)
             self._host_scores = _engine.to_host(dev[:, :self.n_cells])
         return self._host_scores
 
@@ -243,9 +248,9 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
     lists the positions (into ``signatures``) that survived.
 
     ``replicated`` (multi-GPU job: every rank makes this call with the same arguments): the
-    signature list is cut by position into one block per rank; a rank matches, packs and
-    scores its block only, and the kept positions / numGenes of all blocks are exchanged (one
-    small all-reduce), so every rank knows the job's rows."""
+    signature list is dealt round-robin by position to the ranks; a rank matches, packs and
+    scores its share only, and the kept positions / numGenes of all shares are exchanged (one
+    small all-reduce over the host group), so every rank knows the job's rows."""
     if method not in METHODS:
         raise KeyError(method)
     _engine.require_cuda()
@@ -266,14 +271,13 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
             # the kernels index Z with X's rows and leading dimension; the reference fails on the
             # fancy-indexing / broadcast of a mismatched mask (SigScoreMethods.py:101-103, 147)
             raise ValueError("zero_locations shape %s != data shape %s" % (tuple(z.shape), (n_genes, n_cells)))
-    bounds, rank, pos_lo = None, 0, 0
+    owner_rows, rank, world_size = None, 0, 1
     mine = signatures
     if replicated:
         from . import distributed as D
         world_size, rank = D.world()
         if world_size > 1:
-            pos_lo, pos_hi = D.shard_bounds(len(signatures), world_size, rank)
-            mine = signatures[pos_lo:pos_hi]
+            mine = signatures[rank::world_size]
     kept, sig_ptr, sig_gene, sig_sign, counts = pack_signatures(
         mine, data.row_labels, min_signature_genes, raise_on_reject)
     # one upload for the two int32 tables (few, larger host -> device transfers: they share the
@@ -282,20 +286,17 @@ def score_batch(data, signatures, method, zero_locations, min_signature_genes,
     d_ptr, d_gene = d_tables[:sig_ptr.size], d_tables[sig_ptr.size:]
     d_sign = _engine.to_device(sig_sign, torch.int8)
     scores = _engine.score_signatures(method, x, w, z, d_ptr, d_gene, d_sign, len(kept))
-    if replicated and mine is not signatures:
+    if world_size > 1:
         # numGenes by position (0 = rejected), summed over the ranks: the job's kept rows
         from . import distributed as D
         by_pos = np.zeros(len(signatures), dtype=np.int64)
-        by_pos[np.asarray(kept, dtype=np.int64) + pos_lo] = counts
+        by_pos[np.asarray(kept, dtype=np.int64) * world_size + rank] = counts
         # through the host (gloo) group: the launch queue of the GPU keeps running meanwhile
         by_pos = D.all_reduce_sum_host(by_pos)
         all_kept = np.nonzero(by_pos)[0]
-        bounds = []
-        for r in range(world_size):
-            lo, hi = D.shard_bounds(len(signatures), world_size, r)
-            bounds.append((int(np.searchsorted(all_kept, lo)), int(np.searchsorted(all_kept, hi))))
+        owner_rows = D.cyclic_owner_rows(all_kept.size, world_size, positions=all_kept)
         kept, counts = [int(k) for k in all_kept], by_pos[all_kept]
-    batch = ScoreBatch(scores, n_cells, counts, bounds, rank)
+    batch = ScoreBatch(scores, n_cells, counts, owner_rows, rank)
     batch.kept = kept
     return batch
 

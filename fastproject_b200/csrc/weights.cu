@@ -12,7 +12,8 @@
 //   pne_nd   = clip(1 - (1 - pd_e) * pe / pnd, 0, 1)
 //   W        = pne_nd * p_nd + p_d
 //
-// One CTA per gene, three sweeps over the row (the second and third hit L2): the row sums
+// One CTA per gene, three sweeps over the row (the second and third hit L2; the second parks
+// 1 - fn in the output row so that exp and the division run once per element): the row sums
 // follow NumPy's pairwise order (row_tree.cuh) and every operation is rounded separately in
 // the reference's order, so the only difference from the reference is the last-bit freedom of
 // exp() (CUDA's and NumPy's are both within 1 ulp but not identical): weights agree to
@@ -52,11 +53,16 @@ __device__ __forceinline__ double fn_rate(double mu, const double *__restrict__ 
     const double e = exp(__dmul_rn(__dsub_rn(mu, x0), a));
     return __dadd_rn(L, __ddiv_rn(S, __dadd_rn(1.0, e)));
 }
-struct ExpressedDetect {     // pd_e = 1 - fn
+struct ExpressedDetect {     // pd_e = 1 - fn; also parked in the output row for the last sweep
     double mu;
     const double *params;
     long ldp;
-    __device__ double operator()(long i) const { return __dsub_rn(1.0, fn_rate(mu, params, ldp, i)); }
+    double *park;
+    __device__ double operator()(long i) const {
+        const double v = __dsub_rn(1.0, fn_rate(mu, params, ldp, i));
+        park[i] = v;         // (the n % 8 tail of a leaf is evaluated by all eight lanes: same value)
+        return v;
+    }
 };
 
 __global__ void __launch_bounds__(W_THREADS)
@@ -83,7 +89,10 @@ compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ 
         }
         __syncthreads();
         const double mu = stat[0];
-        fp::rowtree::leaf_sums(ExpressedDetect{mu, params, ldp}, leaves, n_leaves, sum_a);
+        double *orow = out + g * ld_out;
+        // the exp and the division of the false-negative curve are evaluated once per element:
+        // this sweep parks 1 - fn in the output row, the last sweep turns it into the weight
+        fp::rowtree::leaf_sums(ExpressedDetect{mu, params, ldp, orow}, leaves, n_leaves, sum_a);
         __syncthreads();
         if (threadIdx.x == 0) {
             const double mean_pde = __ddiv_rn(fold_tree(sum_a, prog, n_prog, stack), (double)N);
@@ -94,11 +103,10 @@ compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ 
         }
         __syncthreads();
         const double pe = stat[1], pnd = stat[2];
-        double *orow = out + g * ld_out;
         for (long c = threadIdx.x; c < N; c += blockDim.x) {
             const double p_nd = p_nd_at(row, prow, c);
             const double p_d = __dsub_rn(1.0, p_nd);
-            const double pd_e = __dsub_rn(1.0, fn_rate(mu, params, ldp, c));
+            const double pd_e = orow[c];
             // 1 - (1 - pd_e) * pe / pnd, evaluated left to right
             double v = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(__dsub_rn(1.0, pd_e), pe), pnd));
             if (v < 0.0) v = 0.0;

@@ -4,12 +4,12 @@
 Every rank is handed the same inputs (expression data, the full signature lists, all
 projections) and returns the same result as a single-GPU run; the work of the job is split:
 
-  stage 1  scoring + ranking : the kept signatures (real and random background alike) are cut
-           into contiguous, balanced row blocks, one per rank (``shard_bounds``).  A rank
-           reads X / W once and writes only its rows.
-  exchange ``all_gather_row_blocks``: the rank rows (float64 [rows x cells]) are all-gathered
-           over NVLink so that every rank can contract any block of signatures against any
-           projection (C2: 560 MB, C3 with 4 000 signatures: 3.2 GB per GPU).
+  stage 1  scoring + ranking : the signatures (real and random background alike) are dealt
+           round-robin to the ranks (``cyclic_owner_rows``): the same number of rows and the same
+           mix of signature sizes everywhere.  A rank reads X / W once and writes only its rows.
+  exchange ``all_gather_owned_rows``: the rank rows (float64 [rows x cells]) are all-gathered
+           over NVLink and put back in job order, so that every rank can contract any block of
+           signatures against any projection (C2: 560 MB, C3 with 4 000 signatures: 3.2 GB).
   stage 2  consistency + medians : the (projection x signature-block) grid -- blocks of 254
            signatures, the row tile of one CTA pair of the tensor-core kernel -- is laid out
            projection-major and cut into ``world`` contiguous runs (``partition_units``).  When
@@ -48,6 +48,47 @@ def shard_bounds(n_rows, world_size, rank):
     base, extra = divmod(int(n_rows), int(world_size))
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def cyclic_owner_rows(n_rows, world_size, positions=None):
+    """Which rows of the job's signature batch each rank scores and ranks: dealt round-robin by
+    POSITION in the caller's signature list (``positions[j]`` = list position of job row j;
+    default: j itself).  Contiguous blocks would hand one rank all the 200-gene background
+    signatures and another all the 5-gene ones (5x the scoring work, and everybody waits for the
+    slowest at the all-gather); round-robin gives every rank the same mix and the same number of
+    rows.  Returns a list of ascending int64 index arrays, one per rank."""
+    pos = np.arange(int(n_rows), dtype=np.int64) if positions is None else np.asarray(positions, dtype=np.int64)
+    return [np.nonzero(pos % world_size == r)[0] for r in range(int(world_size))]
+
+
+def all_gather_owned_rows(local, owner_rows, group=None):
+    """local: this rank's rows (``owner_rows[rank]``, in that order) of a [n_rows x ld] matrix ->
+    the whole matrix in job order on every rank: one all-gather of blocks padded to the widest,
+    then one gather-copy that puts the rows back in order."""
+    world_size, rank = world()
+    if world_size == 1:
+        return local
+    ld = local.shape[1]
+    widest = max(len(r) for r in owner_rows)
+    n_rows = sum(len(r) for r in owner_rows)
+    mine = local
+    if local.shape[0] != widest:
+        mine = torch.zeros((widest, ld), dtype=local.dtype, device=local.device)
+        mine[:local.shape[0]] = local
+    buf = torch.empty((world_size * widest, ld), dtype=local.dtype, device=local.device)
+    all_gather_into(buf, mine.contiguous(), group)
+    src = np.empty(n_rows, dtype=np.int64)
+    for r, rows in enumerate(owner_rows):
+        src[rows] = r * widest + np.arange(len(rows))
+    return buf.index_select(0, _index_to(src, local.device))
+
+
+def _index_to(arr, device):
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if torch.device(device).type != "cuda":
+        return t
+    from . import _engine
+    return _engine.to_device(np.ascontiguousarray(arr), torch.long)
 
 
 def partition_units(n_proj, n_rows, world_size, block=SIG_BLOCK):

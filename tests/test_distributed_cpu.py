@@ -36,6 +36,28 @@ def test_shard_bounds_cover_and_balance():
             assert max(widths) - min(widths) <= 1
 
 
+def test_cyclic_owner_rows_cover_and_balance():
+    for n, w in ((0, 4), (1, 8), (7, 8), (3500, 8), (3500, 2), (19001, 3)):
+        rows = D.cyclic_owner_rows(n, w)
+        assert len(rows) == w
+        allr = np.sort(np.concatenate(rows)) if n else np.zeros(0, dtype=np.int64)
+        assert np.array_equal(allr, np.arange(n))
+        assert max(len(r) for r in rows) - min(len(r) for r in rows) <= 1
+        for r in rows:
+            assert np.all(np.diff(r) > 0)
+    # the job's order: 500 real signatures then the background by size -- contiguous blocks would
+    # give the last rank 5x the genes of the lightest; round-robin gives every rank the same mix
+    genes = np.concatenate([np.full(500, 80), np.repeat([5, 10, 20, 50, 100, 200], 500)])
+    sums = [genes[r].sum() for r in D.cyclic_owner_rows(genes.size, 8)]
+    assert max(sums) / min(sums) < 1.02
+    even = [genes[lo:hi].sum() for lo, hi in D.even_bounds(genes.size, 8)]
+    assert max(even) / min(even) > 4
+    # with rejected signatures the rows follow the POSITIONS in the caller's list
+    positions = np.array([0, 1, 3, 4, 8, 9, 10, 15])
+    rows = D.cyclic_owner_rows(positions.size, 4, positions=positions)
+    assert [list(r) for r in rows] == [[0, 3, 4], [1, 5], [6], [2, 7]]
+
+
 @pytest.mark.parametrize("n_proj,n_rows,world", [
     (6, 3500, 8), (8, 4000, 8), (8, 19000, 8), (4, 3200, 8), (6, 3500, 1), (6, 3500, 2), (6, 3500, 4),
     (1, 10, 8), (3, 254, 2), (2, 255, 3), (5, 0, 4), (0, 100, 2)])
@@ -98,9 +120,16 @@ def _worker(rank, world_size, port, out_dir, bounds_kind):
             cuts = [0, 3, 3 + 20][:world_size] + [n_rows]
             bounds = [(cuts[r], cuts[r + 1]) for r in range(world_size)]
         lo, hi = bounds[rank]
-        # stage 1: rank my rows, gather all
+        # stage 1: rank my rows, gather all -- contiguous blocks (how the expression rows travel) ...
         local = torch.from_numpy(_stand_in_rank(scores[lo:hi]))
         ranks = D.all_gather_row_blocks(local, bounds)
+        # ... and round-robin rows (how the signature rows are dealt): same matrix, job order
+        if bounds_kind == "even":
+            owner = D.cyclic_owner_rows(n_rows, world_size)
+        else:
+            owner = D.cyclic_owner_rows(n_rows, world_size, positions=np.arange(n_rows) * 3 + (np.arange(n_rows) % 2))
+        mine = torch.from_numpy(_stand_in_rank(scores[owner[rank]]))
+        assert torch.equal(D.all_gather_owned_rows(mine, owner), ranks)
         # stage 2: my runs of the (projection x block) grid (tiny blocks so that runs straddle)
         med = torch.zeros((n_proj, n_rows), dtype=torch.float64)
         for p, rlo, rhi in D.partition_units(n_proj, n_rows, world_size, block=5)[rank]:
