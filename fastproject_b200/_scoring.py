@@ -82,13 +82,14 @@ def _match_rows(flat_genes, n_entries, row_labels):
     return rows
 
 
-def _signs_of(flat_vals):
+def _signs_of(dicts, n_entries):
     """+1 for a dict value equal to 1 or 0, -1 for -1, 0 (= ignored) for anything else
     (Signatures.py:750-753); None if the values are not numbers."""
-    kinds = set(flat_vals)
+    kinds = set(itertools.chain.from_iterable(map(dict.values, dicts)))
     try:
         if kinds <= {1, 0}:                       # unsigned lists, every random background list
-            return np.ones(len(flat_vals), dtype=np.int8)
+            return np.ones(n_entries, dtype=np.int8)
+        flat_vals = list(itertools.chain.from_iterable(map(dict.values, dicts)))
         if kinds <= {1, 0, -1}:
             v = np.frombuffer(bytes(map((1).__add__, flat_vals)), dtype=np.uint8).astype(np.int8) - 1
             return np.where(v == 0, 1, v).astype(np.int8)
@@ -113,10 +114,9 @@ def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject
     dicts = [sig.sig_dict for sig in signatures]
     lengths = np.fromiter((len(d) for d in dicts), dtype=np.int64, count=len(dicts))
     n_entries = int(lengths.sum())
-    flat_vals = list(itertools.chain.from_iterable(d.values() for d in dicts))
     rows = _match_rows(itertools.chain.from_iterable(dicts), n_entries, row_labels) if n_entries else \
         np.zeros(0, dtype=np.int32)
-    signs = _signs_of(flat_vals) if rows is not None else None
+    signs = _signs_of(dicts, n_entries) if rows is not None else None
     if rows is None or signs is None:
         return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
     rows = rows.astype(np.int64)
