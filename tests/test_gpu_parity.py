@@ -166,10 +166,15 @@ def test_rank_ties_constant_negative_zero_and_nan(fp):
         fp.M.SignatureScores(["a"], "f", [], True, True, 0).ranks
 
 
-def test_rank_short_keys_hard_cases(fp):
-    """The rank path sorts a short monotone key and orders the cells sharing a key bin by their
-    doubles: exercise every bin regime against scipy (bit-exact), both tie rules."""
+@pytest.mark.parametrize("path", ["fused", "sort"])
+def test_rank_short_keys_hard_cases(fp, path, monkeypatch):
+    """The rank path bins the cells by a short monotone key (rows up to 48 000 cells: a counting
+    sort inside one CTA, "fused"; longer rows, or FASTPROJECT_B200_RANK=sort: a segmented radix
+    sort) and orders the cells sharing a key bin by their doubles: exercise every bin regime
+    against scipy (bit-exact), both tie rules, both paths."""
     import torch
+    if path == "sort":
+        monkeypatch.setenv("FASTPROJECT_B200_RANK", "sort")
     from scipy.stats import rankdata
     from fastproject_b200 import _engine as E, _native
     rng = np.random.RandomState(3)
@@ -204,6 +209,14 @@ def test_rank_short_keys_hard_cases(fp):
     got = E.rank_rows(torch.as_tensor(y).cuda(), 1001).cpu().numpy()
     for i in range(k):
         assert np.array_equal(got[i, :1001], rankdata(y[i, :1001]))
+    # the largest rows of the fused path, one beyond it, and tiny ones
+    for m in (1, 2, 31, 47999, 48000, 48001):
+        z = rng.normal(size=(3, m)); z[1] = np.round(z[1], 2); z[2, : m // 2] = 0.0
+        zd = torch.zeros((3, E.padded(m)), dtype=torch.float64, device="cuda")
+        zd[:, :m] = torch.as_tensor(z).cuda()
+        got = E.rank_rows(zd, m).cpu().numpy()
+        for i in range(3):
+            assert np.array_equal(got[i, :m], rankdata(z[i])), (m, i)
 
 
 def test_small_uploads_bypass_copy_engine_bit_exact(fp):
