@@ -255,30 +255,120 @@ long_bins_warp_kernel(const double *__restrict__ scores, const int32_t *__restri
     }
 }
 
-// one CTA per large mixed bin: every cell counts against the whole bin
+// One CTA per large mixed bin (more than kWarpBin cells whose short keys coincide although their
+// doubles differ: a row squeezed by an outlier, small non-zero values next to an expression
+// column's zeros).  Counting every cell against the whole bin is O(L^2) -- 1e10 compares for a
+// bin of 1e5 cells.  Instead the bin is re-quantised on ITS OWN range [min, max] into kSubBins
+// sub-bins (histogram and prefix in shared memory, members scattered into a second index
+// array), and a cell counts only against the members of its sub-bin: O(L * L / kSubBins) for
+// spread-out values, and all-equal sub-bins (the zeros) are recognised without comparing.  Exact:
+// the sub-key is monotone in the value, ties are still decided on the doubles.
+constexpr int kSubBins = 4096;
+
 __global__ void __launch_bounds__(256)
-long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restrict__ sorted_cell, long ld,
-                     double *__restrict__ out_ranks, long ld_out, int method, const LongBin *__restrict__ big,
-                     const unsigned *__restrict__ big_count) {
+long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restrict__ sorted_cell,
+                     int32_t *__restrict__ scratch_cell, long ld, double *__restrict__ out_ranks, long ld_out,
+                     int method, const LongBin *__restrict__ big, const unsigned *__restrict__ big_count) {
+    __shared__ uint32_t sub[kSubBins + 1];
+    __shared__ uint32_t mixed[kSubBins / 32];            // bit k: sub-bin k holds different values
+    __shared__ double s_mn[8], s_mx[8];
+    __shared__ uint32_t s_part[8];
     const unsigned n_big = *big_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned e = blockIdx.x; e < n_big; e += gridDim.x) {
         const LongBin w = big[e];
         const double *src = scores + (long)w.row * ld;
         const int32_t *cs = sorted_cell + (long)w.row * ld;
+        int32_t *cs2 = scratch_cell + (long)w.row * ld;
         double *out = out_ranks + (long)w.row * ld_out;
         const long a = w.a, L = w.b - w.a;
+        // range of the bin (finite or infinite: bit-pattern sub-keys then)
+        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
+        for (long i = threadIdx.x; i < L; i += blockDim.x) {
+            const double v = src[cs[a + i]];
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+        for (int o = 16; o; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+        for (int k = threadIdx.x; k <= kSubBins; k += blockDim.x) sub[k] = 0;
+        for (int k = threadIdx.x; k < kSubBins / 32; k += blockDim.x) mixed[k] = 0;
+        __syncthreads();
+        for (int k = 0; k < 8; ++k) { mn = fmin(mn, s_mn[k]); mx = fmax(mx, s_mx[k]); }
+        const double span = mx - mn;
+        const double scale = (span > 0.0 && !isinf(span)) ? (double)(kSubBins - 1) / span : 0.0;
+        const bool linear = scale > 0.0 && !isinf(scale);
+        // with bit-pattern keys the leading bits that min and max share carry no information
+        const uint64_t bmn = ordered_bits(mn), bmx = ordered_bits(mx);
+        const int shared_bits = (bmn == bmx) ? 52 : __clzll((long long)(bmn ^ bmx));
+        const int shift = 64 - 12 - (shared_bits < 52 ? shared_bits : 52);
+        auto subkey = [&](double v) -> uint32_t {
+            if (linear) return (uint32_t)__double2ull_rz(fmin((v - mn) * scale, (double)(kSubBins - 1)));
+            const uint64_t rel = ordered_bits(v) - bmn;             // monotone, 0 at the minimum
+            const uint64_t q = shift > 0 ? (rel >> shift) : rel;
+            return (uint32_t)(q < (uint64_t)(kSubBins - 1) ? q : (uint64_t)(kSubBins - 1));
+        };
+        for (long i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(&sub[subkey(src[cs[a + i]])], 1u);
+        __syncthreads();
+        {   // exclusive prefix: thread t owns sub-bins 16 t .. 16 t + 15
+            uint32_t local = 0;
+            uint32_t *mine = sub + threadIdx.x * 16;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) local += mine[k];
+            uint32_t incl = local;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) s_part[warp] = incl;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int k = 0; k < warp; ++k) base += s_part[k];
+            uint32_t run = base + incl - local;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t c = mine[k];
+                mine[k] = run;
+                run += c;
+            }
+            if (threadIdx.x == blockDim.x - 1) sub[kSubBins] = run;
+        }
+        __syncthreads();
+        // members of every sub-bin, contiguous in the scratch index array; afterwards sub[k] = END of sub-bin k
+        for (long i = threadIdx.x; i < L; i += blockDim.x) {
+            const int32_t cell = cs[a + i];
+            cs2[a + atomicAdd(&sub[subkey(src[cell])], 1u)] = cell;
+        }
+        __syncthreads();
+        // a sub-bin whose members all equal its first one (the zeros of an expression column) is one tie run
+        for (long i = threadIdx.x; i < L; i += blockDim.x) {
+            const double v = src[cs[a + i]];
+            const uint32_t k = subkey(v);
+            const double first = src[cs2[a + (k ? sub[k - 1] : 0u)]];
+            if (v != first) atomicOr(&mixed[k >> 5], 1u << (k & 31));
+        }
+        __syncthreads();
         for (long i = threadIdx.x; i < L; i += blockDim.x) {
             const int32_t cell = cs[a + i];
             const double v = src[cell];
-            long less = 0, equal = 0;
-            for (long q = 0; q < L; ++q) {
-                const double u = src[cs[a + q]];
-                less += u < v;
-                equal += u == v;
+            const uint32_t k = subkey(v);
+            const uint32_t lo = k ? sub[k - 1] : 0u, hi = sub[k];
+            long less = 0, equal = hi - lo;
+            if ((mixed[k >> 5] >> (k & 31)) & 1u) {
+                equal = 0;
+                for (uint32_t q = lo; q < hi; ++q) {
+                    const double u = src[cs2[a + q]];
+                    less += u < v;
+                    equal += u == v;
+                }
             }
-            out[cell] = method == FP_RANK_MIN ? (double)(a + less + 1)
-                                              : (double)(a + less) + 0.5 * (double)(equal + 1);
+            const long below = a + lo + less;
+            out[cell] = method == FP_RANK_MIN ? (double)(below + 1) : (double)below + 0.5 * (double)(equal + 1);
         }
+        __syncthreads();
     }
 }
 
@@ -326,6 +416,7 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
         // ---- range and special values (the only read of the row that misses L2)
         double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
         int flag = 0;                                        // bit 0: NaN seen, bit 1: infinity seen
+#pragma unroll 4
         for (long c = tid; c < N; c += kFusedThreads) {
             const double v = src[c];
             if (v != v) flag |= 1;
@@ -365,9 +456,22 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
             continue;
         }
         // ---- histogram of the 16-bit keys (two counters per word)
-        for (long c = tid; c < N; c += kFusedThreads) {
-            const uint32_t q = fused_key(src[c], mode, lo, scale);
-            atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
+        {
+            long c = tid;
+            for (; c + 3 * kFusedThreads < N; c += 4 * kFusedThreads) {       // four loads in flight
+                const double v0 = src[c], v1 = src[c + kFusedThreads], v2 = src[c + 2 * kFusedThreads],
+                             v3 = src[c + 3 * kFusedThreads];
+                const uint32_t q0 = fused_key(v0, mode, lo, scale), q1 = fused_key(v1, mode, lo, scale),
+                               q2 = fused_key(v2, mode, lo, scale), q3 = fused_key(v3, mode, lo, scale);
+                atomicAdd(&cnt[q0 >> 1], (q0 & 1) ? 0x10000u : 1u);
+                atomicAdd(&cnt[q1 >> 1], (q1 & 1) ? 0x10000u : 1u);
+                atomicAdd(&cnt[q2 >> 1], (q2 & 1) ? 0x10000u : 1u);
+                atomicAdd(&cnt[q3 >> 1], (q3 & 1) ? 0x10000u : 1u);
+            }
+            for (; c < N; c += kFusedThreads) {
+                const uint32_t q = fused_key(src[c], mode, lo, scale);
+                atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
+            }
         }
         __syncthreads();
         // ---- exclusive prefix over the 65 536 counters: thread t owns bins 64 t .. 64 t + 63
@@ -403,13 +507,31 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
         }
         __syncthreads();
         // ---- counting sort: the cell numbers in bin order; afterwards a counter holds its bin's END
-        for (long c = tid; c < N; c += kFusedThreads) {
-            const uint32_t q = fused_key(src[c], mode, lo, scale);
-            const uint32_t old = atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
-            order[(old >> ((q & 1) * 16)) & 0xffffu] = (uint16_t)c;
+        {
+            long c = tid;
+            for (; c + 3 * kFusedThreads < N; c += 4 * kFusedThreads) {
+                const double v0 = src[c], v1 = src[c + kFusedThreads], v2 = src[c + 2 * kFusedThreads],
+                             v3 = src[c + 3 * kFusedThreads];
+                const uint32_t q0 = fused_key(v0, mode, lo, scale), q1 = fused_key(v1, mode, lo, scale),
+                               q2 = fused_key(v2, mode, lo, scale), q3 = fused_key(v3, mode, lo, scale);
+                const uint32_t o0 = atomicAdd(&cnt[q0 >> 1], (q0 & 1) ? 0x10000u : 1u);
+                const uint32_t o1 = atomicAdd(&cnt[q1 >> 1], (q1 & 1) ? 0x10000u : 1u);
+                const uint32_t o2 = atomicAdd(&cnt[q2 >> 1], (q2 & 1) ? 0x10000u : 1u);
+                const uint32_t o3 = atomicAdd(&cnt[q3 >> 1], (q3 & 1) ? 0x10000u : 1u);
+                order[(o0 >> ((q0 & 1) * 16)) & 0xffffu] = (uint16_t)c;
+                order[(o1 >> ((q1 & 1) * 16)) & 0xffffu] = (uint16_t)(c + kFusedThreads);
+                order[(o2 >> ((q2 & 1) * 16)) & 0xffffu] = (uint16_t)(c + 2 * kFusedThreads);
+                order[(o3 >> ((q3 & 1) * 16)) & 0xffffu] = (uint16_t)(c + 3 * kFusedThreads);
+            }
+            for (; c < N; c += kFusedThreads) {
+                const uint32_t q = fused_key(src[c], mode, lo, scale);
+                const uint32_t old = atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
+                order[(old >> ((q & 1) * 16)) & 0xffffu] = (uint16_t)c;
+            }
         }
         __syncthreads();
         // ---- ranks, written in cell order
+#pragma unroll 2
         for (long c = tid; c < N; c += kFusedThreads) {
             const double v = src[c];
             const uint32_t q = fused_key(v, mode, lo, scale);
@@ -559,8 +681,8 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
             long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
                                                                       work_count, big, big_count);
             FP_CHECK_LAUNCH("long_bins_warp_kernel");
-            long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, big,
-                                                                     big_count);
+            long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, cell_in, ld, dst, ld, method,
+                                                                     big, big_count);
             FP_CHECK_LAUNCH("long_bins_cta_kernel");
             continue;
         }
@@ -585,7 +707,7 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
         long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
                                                                   work_count, big, big_count);
         FP_CHECK_LAUNCH("long_bins_warp_kernel");
-        long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, big,
+        long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, cell_in, ld, dst, ld, method, big,
                                                                  big_count);
         FP_CHECK_LAUNCH("long_bins_cta_kernel");
     }

@@ -219,6 +219,42 @@ def test_rank_short_keys_hard_cases(fp, path, monkeypatch):
             assert np.array_equal(got[i, :m], rankdata(z[i])), (m, i)
 
 
+@pytest.mark.parametrize("path", ["fused", "sort"])
+def test_rank_large_mixed_bins_are_not_quadratic(fp, path, monkeypatch):
+    """Rows whose cells almost all share one short-key bin although their doubles differ (an
+    outlier squeezes the scale; small counts next to the zeros of an expression column): the bin
+    is re-quantised on its own range, so such a row costs milliseconds, not seconds -- and the
+    ranks stay bit-identical to scipy."""
+    import time
+    import torch
+    from scipy.stats import rankdata
+    from fastproject_b200 import _engine as E, _native
+    if path == "sort":
+        monkeypatch.setenv("FASTPROJECT_B200_RANK", "sort")
+    rng = np.random.RandomState(5)
+    n = 40000
+    rows = [
+        np.r_[1e12, rng.normal(size=n - 1)],                                     # one outlier, 39 999 distinct values in bin 0
+        np.r_[1e12, np.where(rng.rand(n - 1) < 0.6, 0.0, rng.gamma(1.0, size=n - 1))],   # zeros + a tail, squeezed
+        np.r_[1e15, rng.randint(0, 50, size=n - 1).astype(float)],               # small counts: 50 tie runs in one bin
+        np.r_[np.inf, -np.inf, rng.normal(size=n - 2) * 1e-300],                 # bit-pattern keys at both levels
+    ]
+    x = np.ascontiguousarray(np.array(rows))
+    dev = torch.zeros((len(rows), E.padded(n)), dtype=torch.float64, device="cuda")
+    dev[:, :n] = torch.as_tensor(x).cuda()
+    for method, name in ((_native.RANK_AVERAGE, "average"), (_native.RANK_MIN, "min")):
+        E.rank_rows(dev, n, method)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = E.rank_rows(dev, n, method)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        got = got.cpu().numpy()
+        for i, v in enumerate(rows):
+            assert np.array_equal(got[i, :n], rankdata(v, method=name)), (i, name)
+        assert dt < 0.05, "ranking %d squeezed rows took %.3f s" % (len(rows), dt)
+
+
 def test_small_uploads_bypass_copy_engine_bit_exact(fp):
     """Per-call tables go host -> device through fp_pull_host (a kernel reading pinned memory):
     every dtype / odd size must arrive byte for byte, also while a large copy is in flight."""
