@@ -265,10 +265,15 @@ long_bins_warp_kernel(const double *__restrict__ scores, const int32_t *__restri
 // the sub-key is monotone in the value, ties are still decided on the doubles.
 constexpr int kSubBins = 4096;
 
+// A sub-bin that is still large and mixed (zeros next to a few tiny values) becomes a work item of
+// the NEXT round, which re-quantises it on its own, 4 096 times narrower, range: the host launches
+// a fixed number of rounds that ping-pong between the two index arrays and the two work lists; the
+// last round counts whatever is left.
 __global__ void __launch_bounds__(256)
 long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restrict__ sorted_cell,
                      int32_t *__restrict__ scratch_cell, long ld, double *__restrict__ out_ranks, long ld_out,
-                     int method, const LongBin *__restrict__ big, const unsigned *__restrict__ big_count) {
+                     int method, const LongBin *__restrict__ big, const unsigned *__restrict__ big_count,
+                     LongBin *__restrict__ next, unsigned *__restrict__ next_count) {
     __shared__ uint32_t sub[kSubBins + 1];
     __shared__ uint32_t mixed[kSubBins / 32];            // bit k: sub-bin k holds different values
     __shared__ double s_mn[8], s_mx[8];
@@ -313,26 +318,25 @@ long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restric
         };
         for (long i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(&sub[subkey(src[cs[a + i]])], 1u);
         __syncthreads();
-        {   // exclusive prefix: thread t owns sub-bins 16 t .. 16 t + 15
-            uint32_t local = 0;
-            uint32_t *mine = sub + threadIdx.x * 16;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) local += mine[k];
-            uint32_t incl = local;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            if (lane == 31) s_part[warp] = incl;
+        {   // exclusive prefix over the 4 096 sub-bin counts: warp w owns sub-bins 512 w .. 512 w + 511,
+            // 32 consecutive ones per step (lane = counter: no bank conflicts)
+            uint32_t *chunk = sub + warp * 512;
+            uint32_t total = 0;
+            for (int step = 0; step < 16; ++step) total += chunk[step * 32 + lane];
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) s_part[warp] = total;
             __syncthreads();
-            uint32_t base = 0;
-            for (int k = 0; k < warp; ++k) base += s_part[k];
-            uint32_t run = base + incl - local;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t c = mine[k];
-                mine[k] = run;
-                run += c;
+            uint32_t run = 0;
+            for (int k = 0; k < warp; ++k) run += s_part[k];
+            for (int step = 0; step < 16; ++step) {
+                const uint32_t c = chunk[step * 32 + lane];
+                uint32_t incl = c;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                chunk[step * 32 + lane] = run + incl - c;
+                run += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (threadIdx.x == blockDim.x - 1) sub[kSubBins] = run;
         }
@@ -358,6 +362,12 @@ long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restric
             const uint32_t lo = k ? sub[k - 1] : 0u, hi = sub[k];
             long less = 0, equal = hi - lo;
             if ((mixed[k >> 5] >> (k & 31)) & 1u) {
+                if (next && hi - lo > (uint32_t)kWarpBin && hi - lo < (uint32_t)L) {
+                    // still large and mixed: one member files it for the next round (which reads
+                    // the members from the array this round wrote)
+                    if (cs2[a + lo] == cell) next[atomicAdd(next_count, 1u)] = LongBin{w.row, (int)(a + lo), (int)(a + hi), 0};
+                    continue;
+                }
                 equal = 0;
                 for (uint32_t q = lo; q < hi; ++q) {
                     const double u = src[cs2[a + q]];
@@ -387,16 +397,27 @@ long_bins_cta_kernel(const double *__restrict__ scores, const int32_t *__restric
 constexpr int kFusedThreads = 1024;
 constexpr int kFusedBins = 65536;
 constexpr long kFusedMaxCells = 48000;             // 128 KB of counters + 2 bytes per cell <= 227 KB
+constexpr long kFusedSubMaxCells = 24500;          // ... + 2 more bytes per cell for the sub-keys
 static_assert(kFusedBins * 2 + kFusedMaxCells * 2 + 1024 <= 232448, "shared memory of rank_rows_fused_kernel");
+static_assert(kFusedBins * 2 + kFusedSubMaxCells * 4 + 1024 <= 232448, "shared memory of rank_rows_fused_kernel<true>");
 
-__device__ __forceinline__ uint32_t fused_key(double v, int mode, double lo, double scale) {
-    if (mode == 0) return (uint32_t)__double2ull_rz(fmin((v - lo) * scale, 65535.0));
-    return (uint32_t)(ordered_bits(v) >> 48);
+// 32-bit monotone key: the top 16 bits choose the bin, the low 16 bits ("sub-key") order most cells
+// inside a bin without looking at their doubles
+__device__ __forceinline__ uint32_t fused_key32(double v, int mode, double lo, double scale) {
+    if (mode == 0) return (uint32_t)__double2ull_rz(fmin((v - lo) * scale, 4294967295.0));
+    return (uint32_t)(ordered_bits(v) >> 32);
 }
 __device__ __forceinline__ uint32_t half_of(const uint32_t *words, uint32_t k) {
     return (words[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
 }
 
+// SUB: keep the sub-keys of the cells (in bin order) in shared memory.  A cell then decides
+// "below / above" against a bin mate from the sub-keys alone -- the key is monotone, so a smaller
+// sub-key means a smaller double -- and loads the mate's double only when the sub-keys coincide
+// (true ties, or values closer than 2^-32 of the row's range).  Without it every cell of a shared
+// bin (a quarter of the cells at 20 000 cells) issues dependent loads of its mates' doubles, and
+// those chains, not bandwidth, set the time of the kernel (1.35 ms at 3 500 x 20 000).
+template <bool SUB>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, long ld, double *__restrict__ out_ranks,
                        long ld_out, int method, int32_t *__restrict__ cell_sorted, LongBin *__restrict__ work,
@@ -404,6 +425,7 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
     extern __shared__ __align__(16) unsigned char fused_smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(fused_smem);                       // kFusedBins / 2 words
     uint16_t *order = reinterpret_cast<uint16_t *>(fused_smem + kFusedBins * 2);     // N cells in bin order
+    uint16_t *subk = order + ((N + 7) & ~7L);                                        // their sub-keys (SUB)
     __shared__ double s_min[32], s_max[32];
     __shared__ int s_flag[32];
     __shared__ uint32_t s_part[32];
@@ -416,15 +438,24 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
         // ---- range and special values (the only read of the row that misses L2)
         double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
         int flag = 0;                                        // bit 0: NaN seen, bit 1: infinity seen
-#pragma unroll 4
-        for (long c = tid; c < N; c += kFusedThreads) {
-            const double v = src[c];
-            if (v != v) flag |= 1;
-            else {
-                if (isinf(v)) flag |= 2;
-                mn = fmin(mn, v);
-                mx = fmax(mx, v);
+        {
+            auto see = [&](double v) {
+                if (v != v) flag |= 1;
+                else {
+                    if (isinf(v)) flag |= 2;
+                    mn = fmin(mn, v);
+                    mx = fmax(mx, v);
+                }
+            };
+            long c = tid;
+            for (; c + 7 * kFusedThreads < N; c += 8 * kFusedThreads) {       // eight loads in flight (HBM)
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = src[c + u * kFusedThreads];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) see(v[u]);
             }
+            for (; c < N; c += kFusedThreads) see(src[c]);
         }
         for (int o = 16; o; o >>= 1) {
             mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -441,7 +472,7 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
                 flag |= s_flag[w];
             }
             const double span = mx - mn;                     // may overflow to +inf: bit-pattern keys
-            const double scale = (span > 0.0 && !isinf(span)) ? 65535.0 / span : 0.0;
+            const double scale = (span > 0.0 && !isinf(span)) ? 4294967295.0 / span : 0.0;
             s_lo = mn;
             s_scale = scale;                                 // a denormal span overflows it: bit-pattern keys
             s_mode = (flag & 1) ? 2 : ((flag & 2) || isinf(span) || isinf(scale)) ? 1 : 0;
@@ -455,37 +486,39 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
             __syncthreads();
             continue;
         }
-        // ---- histogram of the 16-bit keys (two counters per word)
+        // ---- histogram of the 16-bit bin numbers (two counters per word)
         {
             long c = tid;
             for (; c + 3 * kFusedThreads < N; c += 4 * kFusedThreads) {       // four loads in flight
                 const double v0 = src[c], v1 = src[c + kFusedThreads], v2 = src[c + 2 * kFusedThreads],
                              v3 = src[c + 3 * kFusedThreads];
-                const uint32_t q0 = fused_key(v0, mode, lo, scale), q1 = fused_key(v1, mode, lo, scale),
-                               q2 = fused_key(v2, mode, lo, scale), q3 = fused_key(v3, mode, lo, scale);
+                const uint32_t q0 = fused_key32(v0, mode, lo, scale) >> 16, q1 = fused_key32(v1, mode, lo, scale) >> 16,
+                               q2 = fused_key32(v2, mode, lo, scale) >> 16, q3 = fused_key32(v3, mode, lo, scale) >> 16;
                 atomicAdd(&cnt[q0 >> 1], (q0 & 1) ? 0x10000u : 1u);
                 atomicAdd(&cnt[q1 >> 1], (q1 & 1) ? 0x10000u : 1u);
                 atomicAdd(&cnt[q2 >> 1], (q2 & 1) ? 0x10000u : 1u);
                 atomicAdd(&cnt[q3 >> 1], (q3 & 1) ? 0x10000u : 1u);
             }
             for (; c < N; c += kFusedThreads) {
-                const uint32_t q = fused_key(src[c], mode, lo, scale);
+                const uint32_t q = fused_key32(src[c], mode, lo, scale) >> 16;
                 atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
             }
         }
         __syncthreads();
-        // ---- exclusive prefix over the 65 536 counters: thread t owns bins 64 t .. 64 t + 63
+        // ---- exclusive prefix over the 65 536 counters.  Warp w owns words 1024 w .. 1024 w + 1023
+        // and walks them 32 consecutive words at a time (lane = word: no bank conflicts; a thread
+        // owning 32 consecutive words of its own would hit one bank with all 32 lanes -- measured
+        // with ncu: 70 % of the shared-memory wavefronts of the first version were such conflicts).
         {
-            uint32_t local = 0;
-            uint32_t *mine = cnt + tid * 32;
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) local += (mine[w] & 0xffffu) + (mine[w] >> 16);
-            uint32_t incl = local;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
+            uint32_t *chunk = cnt + warp * 1024;
+            uint32_t total = 0;
+#pragma unroll 4
+            for (int step = 0; step < 32; ++step) {
+                const uint32_t word = chunk[step * 32 + lane];
+                total += (word & 0xffffu) + (word >> 16);
             }
-            if (lane == 31) s_part[warp] = incl;
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) s_part[warp] = total;
             __syncthreads();
             if (warp == 0) {
                 uint32_t v = s_part[lane], acc = v;
@@ -496,63 +529,90 @@ rank_rows_fused_kernel(const double *__restrict__ scores, long rows, long N, lon
                 s_part[lane] = acc - v;                      // exclusive over the warps
             }
             __syncthreads();
-            uint32_t run = s_part[warp] + incl - local;      // first position of bin 64 t
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) {
-                const uint32_t word = mine[w];
-                const uint32_t a = run, b = run + (word & 0xffffu);
-                run = b + (word >> 16);
-                mine[w] = a | (b << 16);                     // positions < 65 536
+            uint32_t run = s_part[warp];                     // first position of this warp's first bin
+            for (int step = 0; step < 32; ++step) {
+                const uint32_t word = chunk[step * 32 + lane];
+                const uint32_t c0 = word & 0xffffu, c1 = word >> 16, both = c0 + c1;
+                uint32_t incl = both;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t start = run + incl - both;    // first position of this word's even bin
+                chunk[step * 32 + lane] = start | ((start + c0) << 16);      // positions < 65 536
+                run += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
         __syncthreads();
         // ---- counting sort: the cell numbers in bin order; afterwards a counter holds its bin's END
         {
+            auto place = [&](long c, double v) {
+                const uint32_t q32 = fused_key32(v, mode, lo, scale);
+                const uint32_t q = q32 >> 16;
+                const uint32_t old = atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
+                const uint32_t pos = (old >> ((q & 1) * 16)) & 0xffffu;
+                order[pos] = (uint16_t)c;
+                if (SUB) subk[pos] = (uint16_t)q32;
+            };
             long c = tid;
             for (; c + 3 * kFusedThreads < N; c += 4 * kFusedThreads) {
                 const double v0 = src[c], v1 = src[c + kFusedThreads], v2 = src[c + 2 * kFusedThreads],
                              v3 = src[c + 3 * kFusedThreads];
-                const uint32_t q0 = fused_key(v0, mode, lo, scale), q1 = fused_key(v1, mode, lo, scale),
-                               q2 = fused_key(v2, mode, lo, scale), q3 = fused_key(v3, mode, lo, scale);
-                const uint32_t o0 = atomicAdd(&cnt[q0 >> 1], (q0 & 1) ? 0x10000u : 1u);
-                const uint32_t o1 = atomicAdd(&cnt[q1 >> 1], (q1 & 1) ? 0x10000u : 1u);
-                const uint32_t o2 = atomicAdd(&cnt[q2 >> 1], (q2 & 1) ? 0x10000u : 1u);
-                const uint32_t o3 = atomicAdd(&cnt[q3 >> 1], (q3 & 1) ? 0x10000u : 1u);
-                order[(o0 >> ((q0 & 1) * 16)) & 0xffffu] = (uint16_t)c;
-                order[(o1 >> ((q1 & 1) * 16)) & 0xffffu] = (uint16_t)(c + kFusedThreads);
-                order[(o2 >> ((q2 & 1) * 16)) & 0xffffu] = (uint16_t)(c + 2 * kFusedThreads);
-                order[(o3 >> ((q3 & 1) * 16)) & 0xffffu] = (uint16_t)(c + 3 * kFusedThreads);
+                place(c, v0);
+                place(c + kFusedThreads, v1);
+                place(c + 2 * kFusedThreads, v2);
+                place(c + 3 * kFusedThreads, v3);
             }
-            for (; c < N; c += kFusedThreads) {
-                const uint32_t q = fused_key(src[c], mode, lo, scale);
-                const uint32_t old = atomicAdd(&cnt[q >> 1], (q & 1) ? 0x10000u : 1u);
-                order[(old >> ((q & 1) * 16)) & 0xffffu] = (uint16_t)c;
-            }
+            for (; c < N; c += kFusedThreads) place(c, src[c]);
         }
         __syncthreads();
-        // ---- ranks, written in cell order
-#pragma unroll 2
-        for (long c = tid; c < N; c += kFusedThreads) {
-            const double v = src[c];
-            const uint32_t q = fused_key(v, mode, lo, scale);
-            const uint32_t b = half_of(cnt, q);
-            const uint32_t a = q ? half_of(cnt, q - 1) : 0u;  // the previous bin's end
-            const uint32_t L = b - a;
-            if (L == 1) {
-                out[c] = (double)(a + 1);
-            } else if (L <= (uint32_t)kShortBin) {
-                int less = 0, equal = 0;
-                for (uint32_t i = a; i < b; ++i) {
-                    const double u = src[order[i]];
-                    less += u < v;
-                    equal += u == v;
+        // ---- ranks, written in cell order (four cells per thread in flight)
+        {
+            auto rank_cell = [&](long c, double v) {
+                const uint32_t q32 = fused_key32(v, mode, lo, scale);
+                const uint32_t q = q32 >> 16;
+                const uint32_t b = half_of(cnt, q);
+                const uint32_t a = q ? half_of(cnt, q - 1) : 0u;  // the previous bin's end
+                const uint32_t L = b - a;
+                if (L == 1) {
+                    out[c] = (double)(a + 1);
+                } else if (L <= (uint32_t)kShortBin) {
+                    int less = 0, equal = 0;
+                    const uint32_t mine = q32 & 0xffffu;
+                    for (uint32_t i = a; i < b; ++i) {
+                        if (SUB) {
+                            const uint32_t theirs = subk[i];
+                            if (theirs != mine) {                 // monotone key: the sub-keys decide
+                                less += theirs < mine;
+                                continue;
+                            }
+                            if (order[i] == (uint16_t)c) {        // myself
+                                ++equal;
+                                continue;
+                            }
+                        }
+                        const double u = src[order[i]];
+                        less += u < v;
+                        equal += u == v;
+                    }
+                    out[c] = method == FP_RANK_MIN ? (double)(a + less + 1)
+                                                   : (double)(a + less) + 0.5 * (double)(equal + 1);
+                } else if (order[a] == (uint16_t)c) {            // one cell of a long bin files it
+                    const unsigned slot = atomicAdd(work_count, 1u);
+                    work[slot] = LongBin{(int)row, (int)a, (int)b, 0};
+                    s_long = 1;
                 }
-                out[c] = method == FP_RANK_MIN ? (double)(a + less + 1) : (double)(a + less) + 0.5 * (double)(equal + 1);
-            } else if (order[a] == (uint16_t)c) {            // one cell of a long bin files it
-                const unsigned slot = atomicAdd(work_count, 1u);
-                work[slot] = LongBin{(int)row, (int)a, (int)b, 0};
-                s_long = 1;
+            };
+            long c = tid;
+            for (; c + 3 * kFusedThreads < N; c += 4 * kFusedThreads) {
+                const double v0 = src[c], v1 = src[c + kFusedThreads], v2 = src[c + 2 * kFusedThreads],
+                             v3 = src[c + 3 * kFusedThreads];
+                rank_cell(c, v0);
+                rank_cell(c + kFusedThreads, v1);
+                rank_cell(c + 2 * kFusedThreads, v2);
+                rank_cell(c + 3 * kFusedThreads, v3);
             }
+            for (; c < N; c += kFusedThreads) rank_cell(c, src[c]);
         }
         __syncthreads();
         if (s_long) {                                        // the long-bin kernels read the bin order from global memory
@@ -604,10 +664,34 @@ Layout layout(long rows, long N, long ld) {
     l.nan_b = align_up((size_t)rows * 4);
     // at most one entry per kShortBin + 1 cells, plus the counter
     l.work_b = align_up(((size_t)rows * ld / (kShortBin + 1) + 1) * sizeof(LongBin) + 256) +
-               align_up(((size_t)rows * ld / (kWarpBin + 1) + 1) * sizeof(LongBin));
+               2 * align_up(((size_t)rows * ld / (kWarpBin + 1) + 1) * sizeof(LongBin));
     l.temp_b = align_up(cub_temp_bytes(rows, N, ld));
     l.total = 4 * l.idx_b + l.nan_b + l.work_b + l.temp_b;
     return l;
+}
+
+// The rounds of long_bins_cta_kernel: list A -> list B -> list A -> (last: no further list).  The index
+// arrays swap roles with the lists: a round reads the members of its bins from the array the
+// previous round wrote.
+cudaError_t long_bin_rounds(const double *src, int32_t *idx_a, int32_t *idx_b, long ld, double *dst, int method,
+                            LongBin *list_a, unsigned *count_a, LongBin *list_b, unsigned *count_b, cudaStream_t st) {
+    constexpr int kRounds = 4;
+    for (int r = 0; r < kRounds; ++r) {
+        const bool last = r == kRounds - 1;
+        if (!last) {
+            cudaError_t err = cudaMemsetAsync(count_b, 0, sizeof(unsigned), st);
+            if (err != cudaSuccess) return err;
+        }
+        long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, idx_a, idx_b, ld, dst, ld, method, list_a, count_a,
+                                                                 last ? nullptr : list_b, last ? nullptr : count_b);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        fp::count_launch();
+        int32_t *ti = idx_a; idx_a = idx_b; idx_b = ti;
+        LongBin *tl = list_a; list_a = list_b; list_b = tl;
+        unsigned *tc = count_a; count_a = count_b; count_b = tc;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace
@@ -653,18 +737,24 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
     LongBin *big = reinterpret_cast<LongBin *>(
         ws + 4 * l.idx_b + l.nan_b + align_up(((size_t)rows * ld / (kShortBin + 1) + 1) * sizeof(LongBin) + 256));
     unsigned *big_count = work_count + 1;
+    LongBin *big2 = reinterpret_cast<LongBin *>(reinterpret_cast<char *>(big) +
+                                                align_up(((size_t)rows * ld / (kWarpBin + 1) + 1) * sizeof(LongBin)));
+    unsigned *big2_count = work_count + 2;
     void *cub_temp = ws + 4 * l.idx_b + l.nan_b + l.work_b;
     cudaStream_t st = fp::as_stream(stream);
     const int bits = key_bits(N);
 
     const char *force = getenv("FASTPROJECT_B200_RANK");            // "sort": the CUB path for every N (tests)
     const bool fused = N <= kFusedMaxCells && !(force && !strcmp(force, "sort"));
-    const size_t fused_smem = (size_t)kFusedBins * 2 + (((size_t)N * 2 + 15) & ~(size_t)15);
+    const bool with_sub = N <= kFusedSubMaxCells;
+    const size_t fused_smem = (size_t)kFusedBins * 2 + (size_t)((N + 7) & ~7L) * (with_sub ? 4 : 2) + 16;
     if (fused) {
         static bool attr_set = false;
         if (!attr_set) {
-            FP_CHECK_CUDA(cudaFuncSetAttribute(rank_rows_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kFusedBins * 2 + (int)kFusedMaxCells * 2 + 16));
+            FP_CHECK_CUDA(cudaFuncSetAttribute(rank_rows_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kFusedBins * 2 + (int)kFusedSubMaxCells * 4 + 64));
+            FP_CHECK_CUDA(cudaFuncSetAttribute(rank_rows_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kFusedBins * 2 + (int)kFusedMaxCells * 2 + 64));
             attr_set = true;
         }
     }
@@ -672,18 +762,20 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
         const long nb = (K - k0 < rows) ? (K - k0) : rows;
         const double *src = scores + k0 * ld;
         double *dst = out_ranks + k0 * ld;
-        FP_CHECK_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(unsigned), st));
+        FP_CHECK_CUDA(cudaMemsetAsync(work_count, 0, 4 * sizeof(unsigned), st));
         if (fused) {
             const long ctas = nb < fp::sm_count() ? nb : fp::sm_count();
-            rank_rows_fused_kernel<<<(unsigned)ctas, kFusedThreads, fused_smem, st>>>(src, nb, N, ld, dst, ld, method,
-                                                                                     cell_sorted, work, work_count);
+            if (with_sub)
+                rank_rows_fused_kernel<true><<<(unsigned)ctas, kFusedThreads, fused_smem, st>>>(
+                    src, nb, N, ld, dst, ld, method, cell_sorted, work, work_count);
+            else
+                rank_rows_fused_kernel<false><<<(unsigned)ctas, kFusedThreads, fused_smem, st>>>(
+                    src, nb, N, ld, dst, ld, method, cell_sorted, work, work_count);
             FP_CHECK_LAUNCH("rank_rows_fused_kernel");
             long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
                                                                       work_count, big, big_count);
             FP_CHECK_LAUNCH("long_bins_warp_kernel");
-            long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, cell_in, ld, dst, ld, method,
-                                                                     big, big_count);
-            FP_CHECK_LAUNCH("long_bins_cta_kernel");
+            FP_CHECK_CUDA(long_bin_rounds(src, cell_sorted, cell_in, ld, dst, method, big, big_count, big2, big2_count, st));
             continue;
         }
         const long cap = (long)fp::sm_count() * 4;
@@ -707,9 +799,7 @@ extern "C" int fp_rank_columns_ex(const double *scores, int64_t K, int64_t N, in
         long_bins_warp_kernel<<<fp::sm_count() * 8, 256, 0, st>>>(src, cell_sorted, ld, dst, ld, method, work,
                                                                   work_count, big, big_count);
         FP_CHECK_LAUNCH("long_bins_warp_kernel");
-        long_bins_cta_kernel<<<fp::sm_count() * 4, 256, 0, st>>>(src, cell_sorted, cell_in, ld, dst, ld, method, big,
-                                                                 big_count);
-        FP_CHECK_LAUNCH("long_bins_cta_kernel");
+        FP_CHECK_CUDA(long_bin_rounds(src, cell_sorted, cell_in, ld, dst, method, big, big_count, big2, big2_count, st));
     }
     return FP_OK;
 }

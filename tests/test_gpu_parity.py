@@ -210,7 +210,7 @@ def test_rank_short_keys_hard_cases(fp, path, monkeypatch):
     for i in range(k):
         assert np.array_equal(got[i, :1001], rankdata(y[i, :1001]))
     # the largest rows of the fused path, one beyond it, and tiny ones
-    for m in (1, 2, 31, 47999, 48000, 48001):
+    for m in (1, 2, 31, 24500, 24501, 47999, 48000, 48001):
         z = rng.normal(size=(3, m)); z[1] = np.round(z[1], 2); z[2, : m // 2] = 0.0
         zd = torch.zeros((3, E.padded(m)), dtype=torch.float64, device="cuda")
         zd[:, :m] = torch.as_tensor(z).cuda()
