@@ -302,7 +302,7 @@ class ResidentJob(object):
         for p, lo, hi in self.runs:
             # the median of this run goes to a side stream and overlaps the next run's weight planes
             dis = E.consistency(self.coords[p], self.sig2, ranks[lo:hi], N, out=self.overlap.buffer(hi - lo),
-                                precision=self.precision, slot="bench")
+                                precision=self.precision, slot="bench", any_cell_order=True)
             mark("consistency")
             self.overlap.median_into(dis, N, self.med_all[p, lo:hi])
         self.overlap.join()

@@ -378,7 +378,7 @@ def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision
             for r in idxs:
                 p, lo, hi = runs[r]
                 dis = _engine.consistency(coords_all[p], sig2, ranks[lo:hi], n, out=overlap.buffer(hi - lo),
-                                          precision="fp64", slot="svp")
+                                          precision="fp64", slot="svp", any_cell_order=True)
                 overlap.median_into(dis, n, med_all[p, lo:hi])
 
     for r, (p, lo, hi) in enumerate(runs):
@@ -387,7 +387,7 @@ def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision
             settle(pending)             # the flag lives in a workspace laid out for that shape
             pending = None
         dis = _engine.consistency(coords_all[p], sig2, view, n, out=overlap.buffer(hi - lo),
-                                  precision=requested, slot="svp")
+                                  precision=requested, slot="svp", any_cell_order=True)   # only the median is taken
         overlap.median_into(dis, n, med_all[p, lo:hi])
         pending = (view, (pending[1] if pending else []) + [r])
     if pending is not None:
@@ -425,7 +425,7 @@ def _precomputed_numeric(sig_scores, coords, sig2, n, precision, compute=True):
     rows[0, :n] = r_dev
     perm_dev = _engine.to_device(np.ascontiguousarray(perm.T), torch.long)   # (R, n)
     rows[1:, :n] = r_dev[perm_dev]
-    dis = _engine.consistency(coords, sig2, rows, n, precision=precision)
+    dis = _engine.consistency(coords, sig2, rows, n, precision=precision, any_cell_order=True)
     med = _engine.row_medians(dis, n)
     p, sd = _single_group_pvalue(med[0], med[1:])
     if sd == 0:

@@ -438,8 +438,10 @@ def normalize_cols(x):
 
 
 def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_ABS_ERROR,
-                precision=None, slot="default"):
+                precision=None, slot="default", any_cell_order=False):
     """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor.
+    ``any_cell_order``: the caller only reduces the rows over the cells (median): the columns may
+    come in the library's own cell order (saves scattered writes on the tensor-core path).
     Asynchronous.  The tensor-core mode refuses values it cannot represent exactly (the output
     is then NaN): ``consistency_refused`` tells, after the calls on a workspace ``slot``."""
     k, ld = ranks.shape
@@ -450,6 +452,8 @@ def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_AB
     scalar = 0.0 if vec is not None else float(sigma_sq)
     nbytes = _native.query("fp_consistency_workspace_bytes", n, k, mode)
     ws, ws_ptr = _workspace(nbytes, ranks.device, slot)
+    if any_cell_order:
+        output_kind |= _native.OUT_ANY_CELL_ORDER
     _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
                  ptr(out), out.stride(0), output_kind, mode, ws_ptr, nbytes, stream_ptr())
     return out

@@ -51,6 +51,7 @@ SIGNATURES = {
 METHOD_CODES = {"naive": 0, "weighted_avg": 1, "imputed": 2, "only_nonzero": 3}
 PRECISION_CODES = {"fp64": 0, "tc": 1}
 OUT_ABS_ERROR, OUT_PREDICTION = 0, 1
+OUT_ANY_CELL_ORDER = 0x200
 RANK_AVERAGE, RANK_MIN = 0, 1
 FP_EUNSUPPORTED = -4
 

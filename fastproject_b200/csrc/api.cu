@@ -66,12 +66,13 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
                  "fp_consistency: bad shape N=%ld K=%ld ld=%ld ld_out=%ld", (long)N, (long)K, (long)ld,
                  (long)ld_out);
     FP_CHECK_ARG(sigma_sq || sigma_sq_scalar > 0.0, "fp_consistency: sigma_sq must be positive");
-    FP_CHECK_ARG(output_kind == FP_OUT_ABS_ERROR || output_kind == FP_OUT_PREDICTION,
+    FP_CHECK_ARG((output_kind & ~FP_OUT_ANY_CELL_ORDER) == FP_OUT_ABS_ERROR ||
+                     (output_kind & ~FP_OUT_ANY_CELL_ORDER) == FP_OUT_PREDICTION,
                  "fp_consistency: unknown output kind %d", output_kind);
     if (K == 0) return FP_OK;
     if (precision_mode == FP_PRECISION_FP64)
         return fp_consistency_fp64(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim,
-                                   ld_out, output_kind, fp::as_stream(stream));
+                                   ld_out, output_kind & ~FP_OUT_ANY_CELL_ORDER, fp::as_stream(stream));
     if (precision_mode == FP_PRECISION_TC)
         return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim, ld_out,
                                  output_kind, workspace, workspace_bytes, fp::as_stream(stream));

@@ -56,6 +56,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "fp_common.cuh"
@@ -294,22 +295,68 @@ nn_search_kernel(const double2 *__restrict__ sorted_xy, const int *__restrict__ 
     nn[sorted_id[t]] = dist_key(best);
 }
 
+// ---------------------------------------------------------------------------
+// Cell order of the contraction.  The sums over the cells j are exact integers, so the cells may
+// be visited in any order; visiting them along a space-filling (Hilbert) curve makes every tile of 128
+// consecutive cells spatially compact, and then whole (cell tile x 128-cell stage) blocks of the
+// weight matrix have all-zero HIGH digit planes (pairs of cells further apart than 0.78 lose the top
+// byte of the 32-bit weight at sigma = 0.33): weight_planes_kernel records which planes of a block
+// are non-zero, and the MMA issuer skips the products of the all-zero ones -- exactly zero
+// contributions, so the result does not change by a bit.
+// ---------------------------------------------------------------------------
+// position of grid point (x, y), 16 bits each, along the Hilbert curve of order 16 (the classic
+// xy -> d walk: one quadrant per step, rotating the frame).  Hilbert rather than Morton order:
+// consecutive cells are always neighbours, so tiles of 128 consecutive cells are more compact
+// (measured on the host, tests/cuda/skip_estimate.py: 1 - 5 % fewer products left than with Z-order).
+__device__ __forceinline__ uint32_t hilbert16(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+#pragma unroll
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) {
+                x = 65535u - x;
+                y = 65535u - y;
+            }
+            const uint32_t t = x;
+            x = y;
+            y = t;
+        }
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+curve_key_kernel(const double *__restrict__ coords, long N, const unsigned long long *__restrict__ bounds,
+                  uint32_t *__restrict__ keys, int32_t *__restrict__ cells) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const NnGrid g = nn_grid_of(bounds, N, 65536);          // the 3-sigma box of the cells, 65 536 steps a side
+    const uint32_t qx = (uint32_t)nn_cell_coord(coords[i], g.xmin, g.inv_hx, 65536);
+    const uint32_t qy = (uint32_t)nn_cell_coord(coords[N + i], g.ymin, g.inv_hy, 65536);
+    keys[i] = hilbert16(qx, qy);
+    cells[i] = (int32_t)i;
+}
+
 __global__ void __launch_bounds__(256)
 cell_setup_kernel(const double *__restrict__ coords, const double *__restrict__ sigma_sq,
                   double sigma_sq_scalar, long N, long Npad, const unsigned long long *__restrict__ nn,
-                  CellI *__restrict__ ci, CellJ *__restrict__ cj, double *__restrict__ table) {
+                  const int32_t *__restrict__ order, CellI *__restrict__ ci, CellJ *__restrict__ cj,
+                  double *__restrict__ table) {
     // 2^(k/128) * (2^32 - 1), 16 interleaved copies: every CTA of weight_planes_kernel copies it
     // into shared memory instead of evaluating 2 048 exp2 of its own
     if (blockIdx.x == 0)
         for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += 256)
             table[idx] = exp2((double)(idx / TAB_COPIES) * (1.0 / TAB)) * 4294967295.0;
-    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;       // position in the contraction's cell order
     if (i >= Npad) return;
     const double *cx = coords, *cy = coords + N;
     const bool live = i < N;
-    const double xi = live ? cx[i] : 0.0, yi = live ? cy[i] : 0.0;
-    const double m = live ? __longlong_as_double((long long)nn[i]) : __longlong_as_double(0x7ff0000000000000LL);
-    const double s2 = sigma_sq ? (live ? sigma_sq[i] : 1.0) : sigma_sq_scalar;
+    const long cell = live ? (order ? (long)order[i] : i) : 0;
+    const double xi = live ? cx[cell] : 0.0, yi = live ? cy[cell] : 0.0;
+    const double m = live ? __longlong_as_double((long long)nn[cell]) : __longlong_as_double(0x7ff0000000000000LL);
+    const double s2 = sigma_sq ? (live ? sigma_sq[cell] : 1.0) : sigma_sq_scalar;
     const double c = 1.4426950408889634074 / s2;             // log2(e) / sigma^2
     CellI a;
     a.c = c;
@@ -402,8 +449,8 @@ __device__ __forceinline__ Digits decode_range(const unsigned long long *__restr
 template <int SR>
 __global__ void __launch_bounds__(256)
 pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, long Kpad, long Npad,
-                   int8_t *__restrict__ planes, const unsigned long long *__restrict__ range,
-                   int *__restrict__ flag) {
+                   const int32_t *__restrict__ order, int8_t *__restrict__ planes,
+                   const unsigned long long *__restrict__ range, int *__restrict__ flag) {
     const Digits dg = decode_range<SR>(range);
     const long R = blockIdx.y;
     const long j4 = ((long)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -423,7 +470,8 @@ pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, l
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (j4 + e >= N) continue;
-            const double v2 = (2.0 * values[sig * ld + j4 + e] - dg.centre2) * dg.scale;
+            const long cell = order ? (long)order[j4 + e] : j4 + e;       // the j-th cell of the contraction
+            const double v2 = (2.0 * values[sig * ld + cell] - dg.centre2) * dg.scale;
             long q = (long)v2;
             if ((double)q != v2 || q > LIMIT || q < -LIMIT) {
                 bad = true;
@@ -472,10 +520,13 @@ __device__ __forceinline__ uint32_t weight_fixed32(double t, const char *__restr
 // compile-time too, so the issuing thread executes little more than the MMAs themselves --
 // with run-time flags and descriptor arithmetic it needed 336 instructions per stage and
 // issued slower (93 clk per MMA) than the tensor core executes (64 clk).
-template <int SR, bool OPEN_CLASSES>
+// TZ: the TZ most significant weight digit planes of this (cell tile x stage) block are all zero
+// (weight_planes_kernel's mask): their products are exactly zero and are not issued.
+template <int SR, bool OPEN_CLASSES, int TZ>
 __device__ __forceinline__ void issue_k_step(uint32_t tmem, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc) {
+    static_assert(!OPEN_CLASSES || TZ == 0, "the first stage of a chunk initialises every class");
 #pragma unroll
-    for (int a = 0; a < WD; ++a)
+    for (int a = TZ; a < WD; ++a)
 #pragma unroll
         for (int b = 0; b < SR; ++b) {
             const int c = a + b;                  // value digit 0 = most significant
@@ -491,6 +542,13 @@ __device__ __forceinline__ void issue_k_step(uint32_t tmem, uint64_t a_desc0, ui
         }
 }
 
+template <int SR, int TZ>
+__device__ __forceinline__ void issue_stage(uint32_t tmem, uint64_t a_st, uint64_t b_st, uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < KS / 32; ++ks)          // K step ks: 32 bytes further along the swizzled rows
+        issue_k_step<SR, false, TZ>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2), idesc);
+}
+
 // ---------------------------------------------------------------------------
 // weight digit planes of a slab of cells i (all j): one thread owns 8 consecutive cells j
 // (their records stay in registers) and walks 32 cells i, so a warp stores 256 contiguous
@@ -503,7 +561,8 @@ constexpr int WG_ROWS = 64;                // cells i per CTA
 // planes[a][i - i_first][j] = digit a (0 = most significant) of W_ij; rows of Npad bytes
 __global__ void __launch_bounds__(WG_THREADS, 3)
 weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj, const double *__restrict__ table,
-                     long i_first, long slab_rows, long plane_rows, long Npad, uint8_t *__restrict__ planes) {
+                     long i_first, long slab_rows, long plane_rows, long Npad, uint8_t *__restrict__ planes,
+                     uint32_t *__restrict__ block_or, int n_stages) {
     __shared__ __align__(16) double tab[TAB * TAB_COPIES];
     __shared__ CellI rows_s[WG_ROWS];
     for (int idx = threadIdx.x; idx < TAB * TAB_COPIES; idx += WG_THREADS) tab[idx] = table[idx];
@@ -522,6 +581,7 @@ weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj,
         jn[e] = r.nb;
     }
     const long rows = min((long)WG_ROWS, slab_rows - r0);
+    uint32_t seen = 0;                        // OR of every weight this thread generates
 #pragma unroll 1
     for (long r = 0; r < rows; ++r) {
         const CellI me = rows_s[r];
@@ -541,6 +601,8 @@ weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj,
                 if (e == dj) w[e] = 0;
         }
 #pragma unroll
+        for (int e = 0; e < WG_COLS; ++e) seen |= w[e];
+#pragma unroll
         for (int a = 0; a < WD; ++a) {
             const uint32_t sel = (3 - a) * 0x11 + 0x40;           // byte (3-a) of x, byte (3-a) of y
             uint2 v;
@@ -549,6 +611,13 @@ weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj,
             *reinterpret_cast<uint2 *>(planes + ((long)a * plane_rows + r0 + r) * Npad + j0) = v;
         }
     }
+    // which digit planes of the (cell tile, stage) block hold anything: byte 3 - a of the OR is plane a.
+    // Sixteen consecutive threads cover one stage of 128 cells j (Npad is a multiple of 128, so a half
+    // warp is in range as a whole).
+    const unsigned active = __activemask();
+    for (int o = 8; o; o >>= 1) seen |= __shfl_xor_sync(active, seen, o);
+    if ((threadIdx.x & 15) == 0 && seen)
+        atomicOr(&block_or[(r0 / TN) * n_stages + j0 / KS], seen);
 }
 
 template <int SR>
@@ -576,7 +645,9 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                        const double *__restrict__ values, long ld, double *__restrict__ out, long ld_out, long N,
                        long K, long Kpad, long i_first, long plane_rows, int n_sig_pairs, int n_items,
                        int n_stages, int chunk_stages, int output_kind,
-                       const unsigned long long *__restrict__ range, const int *__restrict__ flag) {
+                       const unsigned long long *__restrict__ range, const int *__restrict__ flag,
+                       const uint32_t *__restrict__ block_or, const int8_t *__restrict__ value_planes, long Npad,
+                       const int32_t *__restrict__ out_order) {
     using L = MmaSmem<SR>;
     constexpr int STAGES = L::stages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -597,7 +668,8 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);                           // the leader's expect_tx; both CTAs' TMA bytes land on it
+            mbar_init(&full[s], 2);                           // one arrival per CTA's producer (the leader's carries the
+                                                              // expect_tx); both CTAs' TMA bytes land on the leader's
             mbar_init(&empty[s], 1);
         }
         mbar_init(accum_full, 1);
@@ -619,7 +691,6 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         if (lane == 0) {
             // both CTAs' bytes of a stage are counted on the leader's barrier: the leader cannot run
             // ahead of a peer that has not issued its loads, so neither producer is ever lapped
-            constexpr uint32_t tx_bytes = 2 * L::stage_bytes;
             // (Round 2 tried an L2 evict_last hint on the value planes, which every cell tile
             // re-reads: the 140 MB of planes then pushed the weight planes out before their 14
             // readers were through -- 13.1 GB of DRAM reads per launch instead of 9.5, same time:
@@ -628,12 +699,28 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             for (int item = pair; item < n_items; item += n_pairs) {
                 const long tile_row = (long)(item / n_sig_pairs) * TN;       // slab-relative first cell
                 const long blk = (long)(item % n_sig_pairs) * 2 + rank;       // this CTA's block of 127 signatures
+                // the issuer skips the products of all-zero leading weight planes (block_or): those
+                // planes are not loaded either, and a stage with nothing to add loads nothing at all
+                const uint32_t *seen_row = block_or + (long)(item / n_sig_pairs) * n_stages;
+                uint32_t seen_next = __ldg(seen_row);
                 for (int it = 0; it < n_stages; ++it, ++g) {
                     const int s = (int)(g % STAGES);
                     const uint32_t ph = (uint32_t)(g / STAGES) & 1;
+                    const uint32_t seen = seen_next;
+                    if (it + 1 < n_stages) seen_next = __ldg(seen_row + it + 1);
+                    const int tz = (it % chunk_stages == 0) ? 0 : (seen ? (__clz((int)seen) >> 3) : 4);
                     mbar_wait(&empty[s], ph ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(&full[s], tx_bytes);
+                    // both producers arrive on the leader's barrier for EVERY stage (also one that loads
+                    // nothing), and both CTAs' bytes are counted there: the leader cannot run ahead of a
+                    // peer that has not reached the stage, so neither producer is ever lapped
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
+                    if (rank == 0)
+                        mbar_arrive_expect_tx(&full[s], tz == 4 ? 0u
+                                                                : 2u * (uint32_t)(SR * A_PLANE_BYTES +
+                                                                                  (WD - tz) * B_PLANE_BYTES));
+                    else
+                        mbar_arrive_cluster(leader_full);
+                    if (tz == 4) continue;
                     uint8_t *dst = smem + s * L::stage_bytes;
 #pragma unroll
                     for (int b = 0; b < SR; ++b)
@@ -641,8 +728,9 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                                          leader_full);
 #pragma unroll
                     for (int a = 0; a < WD; ++a)
-                        tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
-                                         (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
+                        if (a >= tz)
+                            tma_load_2d_pair(dst + SR * A_PLANE_BYTES + a * B_PLANE_BYTES, &tmap_weights, it * KS,
+                                             (int)(a * plane_rows + tile_row + rank * TNH), leader_full);
                 }
             }
         }
@@ -655,11 +743,18 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             const uint64_t b_desc_base = smem_desc(smem_u32(smem) + SR * A_PLANE_BYTES, 16, 1024, LAYOUT_SW128);
             long g = 0, c = 0;                                // stages / accumulator chunks so far
             for (int item = pair; item < n_items; item += n_pairs) {
+                // non-zero digit planes of this cell tile's blocks, one word per stage (read one stage ahead)
+                const uint32_t *seen_row = block_or + (long)(item / n_sig_pairs) * n_stages;
+                uint32_t seen_next = __ldg(seen_row);
                 for (int it = 0; it < n_stages; ++it, ++g) {
                     const int s = (int)(g % STAGES);
                     const uint32_t ph = (uint32_t)(g / STAGES) & 1;
                     const bool chunk_first = it % chunk_stages == 0;
                     const bool chunk_last = it % chunk_stages == chunk_stages - 1 || it == n_stages - 1;
+                    const uint32_t seen = seen_next;
+                    if (it + 1 < n_stages) seen_next = __ldg(seen_row + it + 1);
+                    // leading all-zero planes: their products are exactly zero (4: nothing to add at all)
+                    const int tz = seen ? (__clz((int)seen) >> 3) : 4;
                     if (chunk_first && c > 0) {
                         mbar_wait_cluster(tmem_empty, (uint32_t)(c - 1) & 1);   // epilogues of both CTAs drained TMEM
                         tc_fence_after_sync();
@@ -670,15 +765,22 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                         const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
                         const uint64_t b_st = b_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
 #ifndef FP_TC_TIMING_NO_MMA
-                        // K step ks: 32 bytes further along the swizzled rows of both operands
-                        if (chunk_first)
-                            issue_k_step<SR, true>(tmem, a_st, b_st, idesc);
-                        else
-                            issue_k_step<SR, false>(tmem, a_st, b_st, idesc);
+                        if (chunk_first) {
+                            // the first stage of a chunk initialises every class: all products
+                            issue_k_step<SR, true, 0>(tmem, a_st, b_st, idesc);
 #pragma unroll
-                        for (int ks = 1; ks < KS / 32; ++ks)
-                            issue_k_step<SR, false>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2),
-                                                    idesc);
+                            for (int ks = 1; ks < KS / 32; ++ks)
+                                issue_k_step<SR, false, 0>(tmem, a_st + (uint64_t)(ks * 2), b_st + (uint64_t)(ks * 2),
+                                                           idesc);
+                        } else {
+                            switch (tz) {
+                                case 0: issue_stage<SR, 0>(tmem, a_st, b_st, idesc); break;
+                                case 1: issue_stage<SR, 1>(tmem, a_st, b_st, idesc); break;
+                                case 2: issue_stage<SR, 2>(tmem, a_st, b_st, idesc); break;
+                                case 3: issue_stage<SR, 3>(tmem, a_st, b_st, idesc); break;
+                                default: break;
+                            }
+                        }
 #endif
                         umma_commit_pair(&empty[s]);          // frees the stage in both CTAs
                         if (chunk_last) umma_commit_pair(accum_full);
@@ -697,6 +799,7 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
         const Digits dg = decode_range<SR>(range);
         // the class sums carry 256^(3-c); the exact product sum is 256^(SR-1) times larger
         const double centre = dg.centre2, inv_scale = (SR == 2 ? 256.0 : 65536.0) / dg.scale;
+        const double unscale = 1.0 / dg.scale;                 // a power of two: exact
         const bool invalid = *flag != 0;
         long c = 0;                                            // accumulator chunks drained so far
 #pragma unroll 1
@@ -782,7 +885,9 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                         const int trow = quad * 32 + rr;
                         const long tsig = blk * SIGS_PER_TILE + trow;
                         if (trow < SIGS_PER_TILE && tsig < K && col < N) {
-                            double *optr = out + tsig * ld_out + col;
+                            // col is a position in the contraction's cell order; the output column is
+                            // that cell's own index unless the caller asked for any order
+                            double *optr = out + tsig * ld_out + (out_order ? (long)out_order[col] : col);
                             // partial sums of earlier j chunks are parked in the output row
                             if (chunk > 0) total += *optr;
                             if (!last) {
@@ -790,7 +895,15 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                             } else {
                                 // total = sum_j W_ij r_j, den = sum_j W_ij; v = (r / scale + centre2) / 2
                                 double r = rden == rden ? 0.5 * (total * rden + centre) : 0.0;
-                                if (output_kind == FP_OUT_ABS_ERROR) r = fabs(values[tsig * ld + col] - r);
+                                if (output_kind == FP_OUT_ABS_ERROR) {
+                                    // the cell's own value, rebuilt exactly from its digits (the value
+                                    // planes are in the contraction's cell order; `values` is not)
+                                    long q = 0;
+#pragma unroll
+                                    for (int b = 0; b < SR; ++b)
+                                        q = q * 256 + (long)value_planes[((long)b * Kpad + blk * TM + trow) * Npad + col];
+                                    r = fabs(0.5 * ((double)q * unscale + centre) - r);
+                                }
                                 if (invalid) r = __longlong_as_double(0x7ff8000000000000LL);
                                 *optr = r;
                             }
@@ -833,6 +946,8 @@ struct Plan {
     long slab_tiles;                             // cell tiles (128 cells i) whose weight planes are resident at once
     int nn_grid;                                 // cells per side of the nearest-neighbour grid (0: brute force)
     size_t nn_xy_off, nn_id_off, nn_cell_off, nn_cnt_off, nn_scan_off, nn_scan_bytes;
+    size_t order_off, zkey_off, zsort_off, zsort_bytes;   // Z-order of the cells (only with the grid: N >= 4 096)
+    size_t seen_off;                                      // non-zero digit planes per (cell tile, stage) of a slab
     size_t planes_off, ci_off, cj_off, nn_off, flag_off, range_off, table_off, weights_off, total;
 };
 
@@ -911,8 +1026,21 @@ bool make_plan(long N, long K, Plan *p) {
         p->nn_scan_bytes = scan_bytes;
         p->nn_scan_off = off;
         off += align_up(scan_bytes, 1024);
+        // Z-order: keys in / out and cell numbers in / out (4 x N words), the order itself, CUB's scratch
+        p->zkey_off = off;
+        off += align_up((size_t)4 * N * 4, 1024);
+        p->order_off = off;
+        off += align_up((size_t)p->Npad * 4, 1024);
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const int32_t *)nullptr, (int32_t *)nullptr, (int)N, 0, 32);
+        p->zsort_bytes = sort_bytes;
+        p->zsort_off = off;
+        off += align_up(sort_bytes, 1024);
     }
     p->slab_tiles = pick_slab_tiles(p->Npad / TN, p->nblk / 2, p->Npad);
+    p->seen_off = off;
+    off += align_up((size_t)p->slab_tiles * (p->Npad / KS) * 4, 1024);
     p->weights_off = off;
     off += align_up((size_t)WD * p->slab_tiles * TN * p->Npad, 1024);
     p->total = off;
@@ -1003,30 +1131,18 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
 
     unsigned long long *range = reinterpret_cast<unsigned long long *>(ws + p.range_off);
     unsigned long long *nn = reinterpret_cast<unsigned long long *>(ws + p.nn_off);
+    const bool any_order = (output_kind & FP_OUT_ANY_CELL_ORDER) != 0;
+    output_kind &= ~FP_OUT_ANY_CELL_ORDER;
+    // FASTPROJECT_B200_NN=brute: the O(N^2) nearest-neighbour kernel; FASTPROJECT_B200_CELL_ORDER=given: no
+    // Z-order (tests compare both with the defaults, bit for bit)
+    const char *nn_env = getenv("FASTPROJECT_B200_NN");
+    const bool brute = nn_env && !strcmp(nn_env, "brute");
+    const char *order_env = getenv("FASTPROJECT_B200_CELL_ORDER");
+    const bool use_grid = p.nn_grid && !brute;
+    const bool z_order = use_grid && !(order_env && !strcmp(order_env, "given"));
+    int32_t *order = z_order ? reinterpret_cast<int32_t *>(ws + p.order_off) : nullptr;
     {
-        // value range and digit planes: re-derived from `values` on every call.  (Round 1 had a
-        // caller-asserted "same values as the previous call" flag that skipped this; a wrong
-        // assertion gave silently wrong results, and verifying it costs as much as packing.)
-        FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
-        FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
-        FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
-        unsigned gy = (unsigned)(K < 296 ? K : 296);
-        unsigned gx = (unsigned)((N + 2047) / 2048);
-        if (gx > 4) gx = 4;
-        value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
-        FP_CHECK_LAUNCH("value_range_kernel");
-        dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
-        if (p.sr == 2)
-            pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
-        else
-            pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, planes, range, flag);
-        FP_CHECK_LAUNCH("pack_values_kernel");
-    }
-    {
-        // FASTPROJECT_B200_NN=brute: the O(N^2) kernel (tests compare the two)
-        const char *nn_env = getenv("FASTPROJECT_B200_NN");
-        const bool brute = nn_env && !strcmp(nn_env, "brute");
-        if (p.nn_grid && !brute) {
+        if (use_grid) {
             const int G = p.nn_grid;
             const size_t cells = (size_t)G * G + 1;
             double2 *sorted_xy = reinterpret_cast<double2 *>(ws + p.nn_xy_off);
@@ -1052,6 +1168,18 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
             nn_search_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(sorted_xy, sorted_id, N, offsets, bounds, G,
                                                                          nn);
             FP_CHECK_LAUNCH("nn_search_kernel");
+            if (z_order) {
+                // the cells along a Z-order curve over the same 3-sigma box: the contraction's cell order
+                uint32_t *zk = reinterpret_cast<uint32_t *>(ws + p.zkey_off);
+                uint32_t *zk_out = zk + N;
+                int32_t *zc = reinterpret_cast<int32_t *>(zk_out + N);
+                curve_key_kernel<<<nb, 256, 0, st>>>(coords, N, bounds, zk, zc);
+                FP_CHECK_LAUNCH("curve_key_kernel");
+                size_t sort_bytes = p.zsort_bytes;
+                FP_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws + p.zsort_off, sort_bytes, zk, zk_out, zc, order, (int)N,
+                                                              0, 32, st));
+                fp::count_launch(4);
+            }
         } else {
             FP_CHECK_CUDA(cudaMemsetAsync(nn, 0x7f, (size_t)p.Npad * 8, st));   // > +inf as a key
             const unsigned bx = (unsigned)((N + 255) / 256);
@@ -1062,9 +1190,29 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
             FP_CHECK_LAUNCH("nearest_neighbour_kernel");
         }
         cell_setup_kernel<<<(unsigned)((p.Npad + 255) / 256), 256, 0, st>>>(coords, sigma_sq, sigma_sq_scalar, N,
-                                                                            p.Npad, nn, ci, cj,
+                                                                            p.Npad, nn, order, ci, cj,
                                                                             reinterpret_cast<double *>(ws + p.table_off));
         FP_CHECK_LAUNCH("cell_setup_kernel");
+    }
+    {
+        // value range and digit planes (in the contraction's cell order): re-derived from `values` on
+        // every call.  (Round 1 had a caller-asserted "same values as the previous call" flag that
+        // skipped this; a wrong assertion gave silently wrong results, and verifying it costs as much
+        // as packing.)
+        FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
+        FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
+        FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
+        unsigned gy = (unsigned)(K < 296 ? K : 296);
+        unsigned gx = (unsigned)((N + 2047) / 2048);
+        if (gx > 4) gx = 4;
+        value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
+        FP_CHECK_LAUNCH("value_range_kernel");
+        dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
+        if (p.sr == 2)
+            pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
+        else
+            pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
+        FP_CHECK_LAUNCH("pack_values_kernel");
     }
     CUtensorMap tmap, tmap_w;
     {
@@ -1109,8 +1257,11 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         const long tiles = n_tiles - t0 < p.slab_tiles ? n_tiles - t0 : p.slab_tiles;
         const long i_first = t0 * TN, slab_rows = tiles * TN;
         dim3 ggrid((unsigned)((p.Npad / WG_COLS + WG_THREADS - 1) / WG_THREADS), (unsigned)(slab_rows / WG_ROWS));
+        uint32_t *seen = reinterpret_cast<uint32_t *>(ws + p.seen_off);
+        FP_CHECK_CUDA(cudaMemsetAsync(seen, 0, (size_t)tiles * n_stages * 4, st));
         weight_planes_kernel<<<ggrid, WG_THREADS, 0, st>>>(ci, cj, reinterpret_cast<const double *>(ws + p.table_off),
-                                                           i_first, slab_rows, plane_rows, p.Npad, wplanes);
+                                                           i_first, slab_rows, plane_rows, p.Npad, wplanes, seen,
+                                                           n_stages);
         FP_CHECK_LAUNCH("weight_planes_kernel");
         // persistent CTA pairs: one per pair of SMs, or fewer when the slab has fewer items
         const int n_sig_pairs = (int)(p.nblk / 2);
@@ -1121,11 +1272,12 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         if (p.sr == 2)
             consistency_mma_kernel<2><<<grid, THREADS, MmaSmem<2>::total, st>>>(
                 tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
-                n_stages, n_stages, output_kind, range, flag);
+                n_stages, n_stages, output_kind, range, flag, seen, planes, p.Npad, any_order ? nullptr : order);
         else
             consistency_mma_kernel<3><<<grid, THREADS, MmaSmem<3>::total, st>>>(
                 tmap, tmap_w, values, ld, out, ld_out, N, K, p.Kpad, i_first, plane_rows, n_sig_pairs, (int)n_items,
-                n_stages, CHUNK_STAGES_3, output_kind, range, flag);
+                n_stages, CHUNK_STAGES_3, output_kind, range, flag, seen, planes, p.Npad,
+                any_order ? nullptr : order);
         FP_CHECK_LAUNCH("consistency_mma_kernel");
     }
     return FP_OK;

@@ -65,6 +65,11 @@ extern "C" {
 /* what fp_consistency writes */
 #define FP_OUT_ABS_ERROR       0   /* |r - prediction|  (Signatures.py:408, 413, 462, 470) */
 #define FP_OUT_PREDICTION      1   /* the prediction itself (factor branch, :493, 505)     */
+/* OR-ed into output_kind: the caller only reduces every output row over the cells (the median of
+ * Signatures.py:409): the columns of out_dissim may come in the library's own cell order (a
+ * Z-order curve on the tensor-core path) instead of the caller's -- same values, same multiset
+ * per row.  Without it the columns are in the caller's order (scattered 8-byte writes). */
+#define FP_OUT_ANY_CELL_ORDER  0x200
 
 /* arithmetic of the neighbourhood contraction in fp_consistency */
 #define FP_PRECISION_FP64      0   /* float64 FMA on the FP64 pipe (verifier)           */

@@ -489,6 +489,40 @@ def test_nearest_neighbour_grid_equals_brute_force(fp, layout, monkeypatch):
     assert np.abs(ref - grid).max() <= 1e-7 * n
 
 
+@pytest.mark.parametrize("n,k,kind", [(6000, 300, 0), (20000, 40, 0), (33000, 5, 0), (6000, 20, 1)])
+def test_z_order_and_plane_skipping_do_not_change_a_bit(fp, n, k, kind, monkeypatch):
+    """From 4 096 cells on the tensor-core path visits the cells along a Z-order curve and skips the
+    products of weight digit planes that are all zero in a (cell tile x stage) block.  Sums of
+    integers in another order, minus terms that are exactly zero: the output is BIT-IDENTICAL to
+    the run in the given cell order, column for column; with FP_OUT_ANY_CELL_ORDER the same
+    values come back in the library's order (same multiset per row, same median)."""
+    import torch
+    from scipy.stats import rankdata
+    from fastproject_b200 import _native
+    rng = np.random.RandomState(n + k)
+    xy = np.concatenate([rng.normal(c, s, size=(n // 4, 2)) for c, s in ((-2, .3), (0, .5), (1.5, .2), (3, .4))])
+    xy = np.concatenate([xy, rng.uniform(-4, 4, size=(n - xy.shape[0], 2))])
+    coords = torch.from_numpy(fp.synth.unit_radius(xy)).cuda()
+    ld = fp.E.padded(n)
+    vals = torch.zeros((k, ld), dtype=torch.float64, device="cuda")
+    if kind == 0:
+        vals[:, :n] = torch.from_numpy(np.array([rankdata(rng.normal(size=n)) for _ in range(k)])).cuda()
+    else:
+        vals[:, :n] = torch.from_numpy((rng.uniform(size=(k, n)) < 0.3).astype(np.float64)).cuda()
+    z = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="tc", output_kind=kind)[:, :n].cpu().numpy()
+    free = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="tc", output_kind=kind,
+                            any_cell_order=True)
+    med_free = fp.E.row_medians(free, n).cpu().numpy()
+    free = free[:, :n].cpu().numpy()
+    monkeypatch.setenv("FASTPROJECT_B200_CELL_ORDER", "given")
+    given = fp.E.consistency(coords, 0.33 ** 2, vals, n, precision="tc", output_kind=kind)[:, :n].cpu().numpy()
+    assert not np.isnan(z).any()
+    assert np.array_equal(z, given)
+    assert np.array_equal(np.sort(free, axis=1), np.sort(given, axis=1))
+    assert not np.array_equal(free, given)                       # it really is another order
+    assert np.array_equal(med_free, np.median(given, axis=1))
+
+
 def test_tensor_core_kernel_binary_predictions(fp):
     a, b = _tc_case(fp, 2000, 300, 5, binary=True, kind=1)
     assert np.abs(a - b).max() <= 1e-8          # values in [0, 1]: the scale puts +-1 in the top digit
