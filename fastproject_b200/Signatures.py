@@ -266,13 +266,6 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     ranks = _device_rank_rows(std_objs + rnd_objs, N_SAMPLES)           # :359-369 (all rows, every rank)
     n_rows = N_SIGNATURES + N_RANDOM
 
-    order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
-                                                [o.numGenes for o in std_objs])
-    d_tables = _engine.to_device(np.concatenate([order, gptr, sig_group]).astype(np.int32), torch.int32)
-    d_order = d_tables[:order.size]
-    d_gptr = d_tables[order.size:order.size + gptr.size]
-    d_group = d_tables[order.size + gptr.size:]
-
     if sigma_per_cell is not None:
         sig2 = _engine.to_device(np.asarray(sigma_per_cell, dtype=np.float64) ** 2)
     else:
@@ -295,6 +288,16 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     if prefetch_next is not None:
         _engine.prefetch(*prefetch_next, replicated=distributed)
 
+    tables = []
+
+    def background_tables():
+        # numGenes bookkeeping of :417-439 (host work, O(signatures)): done while the GPU contracts
+        order, gptr, sig_group = _background_groups([o.numGenes for o in rnd_objs],
+                                                    [o.numGenes for o in std_objs])
+        d_tables = _engine.to_device(np.concatenate([order, gptr, sig_group]).astype(np.int32), torch.int32)
+        tables.extend([d_tables[:order.size], d_tables[order.size:order.size + gptr.size],
+                       d_tables[order.size + gptr.size:]])
+
     # standard signatures, real and random together (:393-446): this rank's runs of the
     # (projection x signature-block) grid -- on one GPU, every projection with all rows
     if world_size > 1:
@@ -304,15 +307,18 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
     med_all = torch.zeros((N_PROJECTIONS, n_rows), dtype=torch.float64, device=dev)
     if my_runs:
         overlap = _engine.MedianOverlap(max(hi - lo for _, lo, hi in my_runs), ranks.shape[1], dev)
-        _contract_runs(my_runs, coords_all, sig2, ranks, N_SAMPLES, overlap, med_all, precision)
+        _contract_runs(my_runs, coords_all, sig2, ranks, N_SAMPLES, overlap, med_all, precision,
+                       while_running=background_tables)
+    if not tables:
+        background_tables()
     if world_size > 1:
         D.all_reduce_sum(med_all)                                       # the one exchange of stage 2
     p_all = torch.empty((N_PROJECTIONS, N_SIGNATURES), dtype=torch.float64, device=dev)
     if N_SIGNATURES:
         for i in range(N_PROJECTIONS):
-            p, _, _ = _engine.background_pvalues(med_all[i, :N_SIGNATURES].contiguous(), d_group,
-                                                 med_all[i, N_SIGNATURES:].contiguous(), d_order,
-                                                 d_gptr)               # :417-442
+            p, _, _ = _engine.background_pvalues(med_all[i, :N_SIGNATURES].contiguous(), tables[2],
+                                                 med_all[i, N_SIGNATURES:].contiguous(), tables[0],
+                                                 tables[1])            # :417-442
             p_all[i] = p
 
     for i, proj in enumerate(sp_col_labels):
@@ -357,7 +363,7 @@ def sigs_vs_projections(projections, sig_scores_dict, random_sig_scores_dict,
             random_sig_proj_matrix, random_sig_score_keys)
 
 
-def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision):
+def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision, while_running=None):
     """med_all[p, lo:hi] = median over cells of |rank - neighbourhood prediction| for every
     run (projection p, rows lo..hi) -- :396-414.  The median of one run is taken on a side stream
     while the next run's weight planes are generated (``_engine.MedianOverlap``).  The tensor-core
@@ -390,6 +396,8 @@ def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision
                                   precision=requested, slot="svp", any_cell_order=True)   # only the median is taken
         overlap.median_into(dis, n, med_all[p, lo:hi])
         pending = (view, (pending[1] if pending else []) + [r])
+    if while_running is not None:
+        while_running()                 # host bookkeeping of the caller, while the queue drains
     if pending is not None:
         settle(pending)
     overlap.join()
