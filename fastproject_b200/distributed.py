@@ -91,17 +91,51 @@ def _index_to(arr, device):
     return _engine.to_device(np.ascontiguousarray(arr), torch.long)
 
 
-def partition_units(n_proj, n_rows, world_size, block=SIG_BLOCK):
+RUN_OVERHEAD = 2.5       # what a rank pays per projection it touches, in units of one signature block:
+                         # weight planes + value packing + cell order, ~1.0 ms against 0.39 ms per
+                         # block at 20 000 cells (measured, C2 on 8 GPUs)
+
+
+def partition_units(n_proj, n_rows, world_size, block=SIG_BLOCK, run_overhead=RUN_OVERHEAD):
     """(projection x signature-block) units, projection-major, cut into ``world_size``
-    contiguous runs of (nearly) equal length.  Returns, per rank, a list of
-    ``(projection, row_lo, row_hi)`` -- the units of one projection merged into one row range,
-    so a rank calls the contraction once per projection it touches."""
+    contiguous runs of (nearly) equal COST: a unit costs 1, and every projection a rank touches
+    costs it ``run_overhead`` more (its weight planes are generated per rank) -- so a rank whose
+    run straddles two projections gets fewer units than one that stays inside a projection.  The
+    cut minimises the largest cost (bisection on the bound, greedy feasibility).  Returns, per
+    rank, a list of ``(projection, row_lo, row_hi)`` -- the units of one projection merged into one
+    row range, so a rank calls the contraction once per projection it touches."""
     n_proj, n_rows, world_size = int(n_proj), int(n_rows), int(world_size)
     n_blocks = (n_rows + block - 1) // block
     total = n_proj * n_blocks
+
+    def cuts_for(bound):
+        """Greedy: give each rank as many consecutive units as fit under ``bound``."""
+        cuts, u = [0], 0
+        for _ in range(world_size):
+            cost, start = 0.0, u
+            while u < total:
+                first_of_projection = (u == start) or (u % n_blocks == 0)
+                step = 1.0 + (run_overhead if first_of_projection else 0.0)
+                if cost + step > bound + 1e-9 and u > start:
+                    break
+                cost += step
+                u += 1
+            cuts.append(u)
+        return cuts if u == total else None
+
+    if total == 0:
+        return [[] for _ in range(world_size)]
+    lo_b, hi_b = 0.0, float(total) + run_overhead * (n_proj + world_size)
+    for _ in range(50):
+        mid = 0.5 * (lo_b + hi_b)
+        if cuts_for(mid) is None:
+            lo_b = mid
+        else:
+            hi_b = mid
+    cuts = cuts_for(hi_b)
     out = []
     for r in range(world_size):
-        lo, hi = shard_bounds(total, world_size, r)
+        lo, hi = cuts[r], cuts[r + 1]
         runs = []
         u = lo
         while u < hi:
