@@ -296,7 +296,7 @@ class ResidentJob(object):
         ranks = E.rank_rows(scores, N)
         mark("rank")
         if self.world > 1:
-            ranks = D.all_gather_owned_rows(ranks, self.owner_rows)
+            ranks = D.all_gather_rank_rows(ranks, self.owner_rows, N)
             self.med_all.zero_()
         mark("gather")
         for p, lo, hi in self.runs:

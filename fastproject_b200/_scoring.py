@@ -212,7 +212,7 @@ class ScoreBatch(object):
             local = self.local_ranks_dev()
             if self.owner_rows is not None:
                 from . import distributed as D
-                local = D.all_gather_owned_rows(local, self.owner_rows)
+                local = D.all_gather_rank_rows(local, self.owner_rows, self.n_cells)
             self._ranks_dev = local
         return self._ranks_dev
 

@@ -83,6 +83,18 @@ def all_gather_owned_rows(local, owner_rows, group=None):
     return buf.index_select(0, _index_to(src, local.device))
 
 
+def all_gather_rank_rows(local_ranks, owner_rows, n_cells, group=None):
+    """``all_gather_owned_rows`` for average ranks: they are integers or half-integers up to
+    ``n_cells``, exactly representable in float32 below 2^22 cells, so half the bytes cross NVLink
+    and the rows are widened back to float64 on arrival (bit-identical)."""
+    world_size, _ = world()
+    if world_size == 1:
+        return local_ranks
+    if int(n_cells) < (1 << 22) and local_ranks.dtype == torch.float64:
+        return all_gather_owned_rows(local_ranks.to(torch.float32), owner_rows, group).to(torch.float64)
+    return all_gather_owned_rows(local_ranks, owner_rows, group)
+
+
 def _index_to(arr, device):
     t = torch.from_numpy(np.ascontiguousarray(arr))
     if torch.device(device).type != "cuda":

@@ -133,6 +133,11 @@ def _worker(rank, world_size, port, out_dir, bounds_kind):
             owner = D.cyclic_owner_rows(n_rows, world_size, positions=np.arange(n_rows) * 3 + (np.arange(n_rows) % 2))
         mine = torch.from_numpy(_stand_in_rank(scores[owner[rank]]))
         assert torch.equal(D.all_gather_owned_rows(mine, owner), ranks)
+        # average ranks travel as float32 (exact for integers and halves) and arrive as float64
+        halves = mine + 0.5 * (mine % 2)
+        got32 = D.all_gather_rank_rows(halves, owner, scores.shape[1])
+        assert got32.dtype == torch.float64
+        assert torch.equal(got32, D.all_gather_owned_rows(halves, owner))
         # stage 2: my runs of the (projection x block) grid (tiny blocks so that runs straddle)
         med = torch.zeros((n_proj, n_rows), dtype=torch.float64)
         for p, rlo, rhi in D.partition_units(n_proj, n_rows, world_size, block=5)[rank]:
