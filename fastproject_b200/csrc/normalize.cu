@@ -23,7 +23,8 @@
 namespace {
 
 using fp::rowtree::Leaf;
-using fp::rowtree::fold_tree;
+using fp::rowtree::Node;
+using fp::rowtree::fold_levels;
 using fp::rowtree::build_tree;
 using fp::rowtree::MAX_DEPTH;
 using fp::rowtree::align_up;
@@ -45,29 +46,67 @@ constexpr int ROW_THREADS = 256;
 
 __global__ void __launch_bounds__(ROW_THREADS)
 row_zscore_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out,
-                  const Leaf *__restrict__ leaves, int n_leaves, const int *__restrict__ prog, int n_prog) {
-    extern __shared__ double leaf_sum[];                 // n_leaves
-    __shared__ double stack[MAX_DEPTH];
-    __shared__ double stat[2];
+                  const Leaf *__restrict__ leaves, int n_leaves, const Node *__restrict__ nodes, int height) {
+    extern __shared__ double val[];                      // 2 * n_leaves
     for (long g = blockIdx.x; g < G; g += gridDim.x) {
         const double *row = X + g * ld;
-        fp::rowtree::leaf_sums(RowLoad{row}, leaves, n_leaves, leaf_sum);
+        fp::rowtree::leaf_sums(RowLoad{row}, leaves, n_leaves, val);
         __syncthreads();
-        if (threadIdx.x == 0) stat[0] = __ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N);
+        const double mean = __ddiv_rn(fold_levels(val, nodes, n_leaves, height), (double)N);
+        fp::rowtree::leaf_sums(RowSqDev{row, mean}, leaves, n_leaves, val);
         __syncthreads();
-        const double mean = stat[0];
-        fp::rowtree::leaf_sums(RowSqDev{row, mean}, leaves, n_leaves, leaf_sum);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double sd = sqrt(__ddiv_rn(fold_tree(leaf_sum, prog, n_prog, stack), (double)N));
-            if (sd == 0.0) sd = 1.0;                      // data_sigma[data_sigma == 0] = 1.0
-            stat[1] = sd;
-        }
-        __syncthreads();
-        const double sd = stat[1];
+        double sd = sqrt(__ddiv_rn(fold_levels(val, nodes, n_leaves, height), (double)N));
+        if (sd == 0.0) sd = 1.0;                          // data_sigma[data_sigma == 0] = 1.0
         double *orow = out + g * ld_out;
         for (long c = threadIdx.x; c < N; c += blockDim.x) orow[c] = __ddiv_rn(__dsub_rn(row[c], mean), sd);
         __syncthreads();
+    }
+}
+
+// Rows that fit in shared memory (N <= ~28 000 cells): the row is staged once by bulk
+// asynchronous copies (row_tree.cuh), both tree sums and the final sweep read it from there, and
+// the next row of the CTA is prefetched into L2 meanwhile -- DRAM sees one read and one write of
+// the matrix (the kernel above re-reads each row twice, and with enough rows in flight to cover
+// the latency they do not all stay in L2: 6.1 GB read for a 2.4 GB matrix).
+constexpr int STAGED_THREADS = 1024;
+
+__global__ void __launch_bounds__(STAGED_THREADS)
+row_zscore_staged_kernel(const double *__restrict__ X, long G, long N, long ld, double *__restrict__ out, long ld_out,
+                         const Leaf *__restrict__ leaves, int n_leaves, const Node *__restrict__ nodes, int height) {
+    extern __shared__ __align__(16) double sm[];         // row (N rounded up to even) | 2 * n_leaves
+    __shared__ uint64_t bar;
+    double *row = sm, *val = sm + ((N + 1) & ~1L);
+    const long n_bulk = N & ~1L;                         // bulk copies move multiples of 16 bytes
+    if (threadIdx.x == 0) {
+        fp::rowtree::stage_init(&bar);
+        if (n_bulk && blockIdx.x < G) fp::rowtree::stage_row_async(row, X + blockIdx.x * ld, (uint32_t)(n_bulk * 8), &bar);
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (long g = blockIdx.x; g < G; g += gridDim.x) {
+        const double *src = X + g * ld;
+        const long next = g + gridDim.x;
+        if (threadIdx.x == 32 && next < G && n_bulk) fp::rowtree::prefetch_row_l2(X + next * ld, (uint32_t)(n_bulk * 8));
+        if (n_bulk) {
+            fp::rowtree::stage_wait(&bar, parity);
+            parity ^= 1;
+        }
+        if (N & 1) {
+            if (threadIdx.x == 0) row[N - 1] = src[N - 1];
+            __syncthreads();
+        }
+        fp::rowtree::leaf_sums(RowLoad{row}, leaves, n_leaves, val);
+        __syncthreads();
+        const double mean = __ddiv_rn(fold_levels(val, nodes, n_leaves, height), (double)N);
+        fp::rowtree::leaf_sums(RowSqDev{row, mean}, leaves, n_leaves, val);
+        __syncthreads();
+        double sd = sqrt(__ddiv_rn(fold_levels(val, nodes, n_leaves, height), (double)N));
+        if (sd == 0.0) sd = 1.0;
+        double *orow = out + g * ld_out;
+        for (long c = threadIdx.x; c < N; c += blockDim.x) orow[c] = __ddiv_rn(__dsub_rn(row[c], mean), sd);
+        __syncthreads();                                  // the row buffer is free again
+        if (threadIdx.x == 0 && next < G && n_bulk)
+            fp::rowtree::stage_row_async(row, X + next * ld, (uint32_t)(n_bulk * 8), &bar);
     }
 }
 
@@ -138,34 +177,52 @@ extern "C" int fp_normalize_rows(const double *X, int64_t G, int64_t N, int64_t 
     std::vector<int> prog;
     int max_depth = 0;
     build_tree(0, N, leaves, prog, 1, max_depth);
-    if (max_depth + 1 > MAX_DEPTH || leaves.size() * 8 > 200 * 1024) {
-        fp::set_error("fp_normalize_rows: rows of %ld cells need %zu tree leaves (limit 25600)", (long)N,
+    if (max_depth + 1 > MAX_DEPTH || leaves.size() * 16 > 200 * 1024) {
+        fp::set_error("fp_normalize_rows: rows of %ld cells need %zu tree leaves (limit 12800)", (long)N,
                       leaves.size());
         return FP_EUNSUPPORTED;
     }
-    const size_t leaves_b = align_up(leaves.size() * sizeof(Leaf)), prog_b = align_up(prog.size() * sizeof(int));
-    if (!workspace || workspace_bytes < leaves_b + prog_b) {
-        fp::set_error("fp_normalize_rows: workspace %zu bytes < required %zu", workspace_bytes, leaves_b + prog_b);
+    const size_t leaves_b = align_up(leaves.size() * sizeof(Leaf)), prog_b = align_up(prog.size() * sizeof(int)),
+                 nodes_b = align_up(leaves.size() * sizeof(Node));
+    if (!workspace || workspace_bytes < leaves_b + prog_b + nodes_b) {
+        fp::set_error("fp_normalize_rows: workspace %zu bytes < required %zu", workspace_bytes,
+                      leaves_b + prog_b + nodes_b);
         return FP_EWORKSPACE;
     }
     cudaStream_t st = fp::as_stream(stream);
     char *ws = static_cast<char *>(workspace);
-    fp::rowtree::build_tree_kernel<<<1, 32, 0, st>>>(N, reinterpret_cast<Leaf *>(ws),
-                                                     reinterpret_cast<int *>(ws + leaves_b));
+    const Leaf *d_leaves = reinterpret_cast<const Leaf *>(ws);
+    const Node *d_nodes = reinterpret_cast<const Node *>(ws + leaves_b + prog_b);
+    fp::rowtree::build_tree_kernel<<<1, 32, 0, st>>>(N, reinterpret_cast<Leaf *>(ws), reinterpret_cast<int *>(ws + leaves_b),
+                                                     reinterpret_cast<Node *>(ws + leaves_b + prog_b));
     FP_CHECK_LAUNCH("build_tree_kernel");              // the host copy above only sized the tables
-    const size_t smem = leaves.size() * sizeof(double);
+    const int height = max_depth - 1;
+    const size_t val_b = 2 * leaves.size() * sizeof(double);
+    const size_t staged_b = (size_t)((N + 1) & ~1L) * sizeof(double) + val_b;
+    if (fp::rowtree::stage_applies(X, ld, staged_b)) {
+        static size_t staged_set = 0;
+        if (staged_b > staged_set) {
+            FP_CHECK_CUDA(cudaFuncSetAttribute(row_zscore_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)staged_b));
+            staged_set = staged_b;
+        }
+        long blocks = (long)fp::sm_count() * (staged_b <= 100 * 1024 ? 2 : 1);
+        if (blocks > G) blocks = G;
+        row_zscore_staged_kernel<<<(unsigned)blocks, STAGED_THREADS, staged_b, st>>>(X, G, N, ld, out, ld_out, d_leaves,
+                                                                                      (int)leaves.size(), d_nodes, height);
+        FP_CHECK_LAUNCH("row_zscore_staged_kernel");
+        return FP_OK;
+    }
     static size_t smem_set = 0;
-    if (smem > 40 * 1024 && smem > smem_set) {
-        FP_CHECK_CUDA(cudaFuncSetAttribute(row_zscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-        smem_set = smem;
+    if (val_b > 40 * 1024 && val_b > smem_set) {
+        FP_CHECK_CUDA(cudaFuncSetAttribute(row_zscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)val_b));
+        smem_set = val_b;
     }
     long blocks = G;
-    const long cap = (long)fp::sm_count() * 8;
+    const long cap = (long)fp::sm_count() * 4;         // rows in flight stay within L2 for the re-reads
     if (blocks > cap) blocks = cap;
-    row_zscore_kernel<<<(unsigned)blocks, ROW_THREADS, smem, st>>>(
-        X, G, N, ld, out, ld_out, reinterpret_cast<const Leaf *>(ws), (int)leaves.size(),
-        reinterpret_cast<const int *>(ws + leaves_b), (int)prog.size());
+    row_zscore_kernel<<<(unsigned)blocks, ROW_THREADS, val_b, st>>>(X, G, N, ld, out, ld_out, d_leaves,
+                                                                    (int)leaves.size(), d_nodes, height);
     FP_CHECK_LAUNCH("row_zscore_kernel");
     return FP_OK;
 }

@@ -7,6 +7,10 @@
 // enumerates its leaves once per call; on the device one thread sums a leaf
 // (fp::np_pairwise_sum) and one thread folds the leaf sums with the tree's post-order program.
 #pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <vector>
 
 #include "fp_common.cuh"
@@ -88,9 +92,104 @@ __device__ inline void build_tree_device(long lo, long n, Leaf *leaves, int *n_l
     if (n_prog) *n_prog = np;
 }
 
-// one thread fills the leaf table and the program of rows of N elements in the workspace
-static __global__ void build_tree_kernel(long N, Leaf *leaves, int *prog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) build_tree_device(0, N, leaves, nullptr, prog, nullptr);
+// The fold as a table of internal nodes for a whole CTA: node k (post-order) adds the value
+// slots l and r into slot n_leaves + k; h is its height (1 = both children are leaves).  Nodes
+// of one height are independent, so the CTA folds level by level (fold_levels) instead of one
+// thread walking the post-order program: same additions, same operands, same order of operands.
+struct Node {
+    int l, r, h, pad;
+};
+
+__device__ inline void build_nodes_device(const int *prog, int n_prog, int n_leaves, Node *nodes) {
+    int sid[MAX_DEPTH], sh[MAX_DEPTH];
+    int sp = 0, k = 0;
+    for (int p = 0; p < n_prog; ++p) {
+        const int op = prog[p];
+        if (op >= 0) {
+            sid[sp] = op; sh[sp] = 0; ++sp;
+        } else {
+            const int b = --sp, a = --sp;
+            const int h = (sh[a] > sh[b] ? sh[a] : sh[b]) + 1;
+            nodes[k] = Node{sid[a], sid[b], h, 0};
+            sid[sp] = n_leaves + k; sh[sp] = h; ++sp;
+            ++k;
+        }
+    }
+}
+
+// val[0 .. n_leaves) holds the leaf sums (written before a __syncthreads()); returns the root to
+// every thread.  All threads of the CTA must call it; val needs 2 * n_leaves slots.
+__device__ __forceinline__ double fold_levels(double *val, const Node *__restrict__ nodes, int n_leaves, int height) {
+    const int n_int = n_leaves - 1;
+    const Node mine = (int)threadIdx.x < n_int ? nodes[threadIdx.x] : Node{0, 0, 0, 0};
+    for (int h = 1; h <= height; ++h) {
+        if (mine.h == h) val[n_leaves + threadIdx.x] = __dadd_rn(val[mine.l], val[mine.r]);
+        for (int k = threadIdx.x + blockDim.x; k < n_int; k += blockDim.x) {
+            const Node nd = nodes[k];
+            if (nd.h == h) val[n_leaves + k] = __dadd_rn(val[nd.l], val[nd.r]);
+        }
+        __syncthreads();
+    }
+    return n_int ? val[n_leaves + n_int - 1] : val[0];
+}
+
+// one thread fills the leaf table, the program and the node table of rows of N elements
+static __global__ void build_tree_kernel(long N, Leaf *leaves, int *prog, Node *nodes) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int n_leaves = 0, n_prog = 0;
+        build_tree_device(0, N, leaves, &n_leaves, prog, &n_prog);
+        if (nodes) build_nodes_device(prog, n_prog, n_leaves, nodes);
+    }
+}
+
+// ---- a whole row staged in shared memory (rows that fit: one CTA per SM, one DRAM read) ------
+// One thread queues the row as bulk asynchronous copies (TMA, 1-D) that complete on an mbarrier;
+// the NEXT row of the CTA is pulled into L2 meanwhile.  Rows must start on 16-byte boundaries.
+constexpr uint32_t STAGE_CHUNK = 32768;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// thread-0 side: bytes is a multiple of 16
+__device__ __forceinline__ void stage_row_async(double *dst, const double *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += STAGE_CHUNK) {
+        const uint32_t n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(dst) + off),
+                     "l"(reinterpret_cast<const char *>(src) + off), "r"(n), "r"(smem_addr(bar))
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void prefetch_row_l2(const double *src, uint32_t bytes) {
+    for (uint32_t off = 0; off < bytes; off += STAGE_CHUNK) {
+        const uint32_t n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(src) + off),
+                     "r"(n)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FP_STAGE_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FP_STAGE_DONE;\n\t"
+        "bra FP_STAGE_WAIT;\n\t"
+        "FP_STAGE_DONE:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// host side: does the staged kernel apply?  (FASTPROJECT_B200_ROW_STAGE=off keeps the kernels
+// that read the rows from global memory -- both give the same bits; tests run both)
+inline bool stage_applies(const void *X, long ld, size_t smem_bytes) {
+    const char *env = getenv("FASTPROJECT_B200_ROW_STAGE");
+    if (env && strcmp(env, "off") == 0) return false;
+    return (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (ld % 2 == 0) && smem_bytes <= 224 * 1024;
 }
 
 inline void build_tree(long lo, long n, std::vector<Leaf> &leaves, std::vector<int> &prog, int depth, int &max_depth) {
@@ -112,7 +211,8 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // bytes of device workspace for the leaves + program of rows of N elements
 inline size_t workspace_bytes(long N) {
     const size_t max_leaves = (size_t)(N / 32 + 2);
-    return align_up(max_leaves * sizeof(Leaf)) + align_up(2 * max_leaves * sizeof(int)) + 256;
+    return align_up(max_leaves * sizeof(Leaf)) + align_up(2 * max_leaves * sizeof(int)) +
+           align_up(max_leaves * sizeof(Node)) + 256;
 }
 
 }  // namespace rowtree

@@ -711,6 +711,45 @@ def test_compute_weights_vs_reference_golden(fp, tag):
         T.compute_weights(lambda v, x0, a, L=0, S=1: np.tanh(v), params, x)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("g,n", [(5, 1), (7, 7), (9, 8), (33, 129), (40, 1001), (64, 4097), (300, 20000), (37, 19999)])
+def test_row_kernels_staged_in_shared_memory_equal_the_global_memory_ones(fp, g, n, monkeypatch):
+    """Rows that fit in shared memory are staged there once (bulk asynchronous copies) by
+    fp_normalize_rows and fp_compute_weights; longer rows, rows on odd pitches and an explicit
+    p_nd take the kernels that read global memory.  Same tree, same operations: BIT-IDENTICAL,
+    and both equal the oracle (bit for bit for the z-scores, 1e-12 for the weights)."""
+    import torch
+    from fastproject_b200 import _engine as E
+    rng = np.random.RandomState(100 + n)
+    x = np.log1p(rng.gamma(0.6, 5.0, size=(g, n))) * (rng.uniform(size=(g, n)) < 0.5)
+    x[0] = 0.0                                            # never detected: NaN weights, sigma -> 1
+    if g > 2:
+        x[1] = 3.25                                       # always detected, constant
+    params = np.vstack([rng.uniform(0.5, 4.0, size=n), rng.uniform(0.0, 2.0, size=n), np.zeros(n), np.ones(n)])
+    xd = E.alloc_matrix(g, n, "cuda")                      # even pitch also when n is odd
+    xd.copy_(torch.from_numpy(x))
+    pd_ = torch.from_numpy(params).cuda()
+    z_staged = E.normalize_rows(xd).cpu().numpy()[:, :n]
+    w_staged = E.compute_weights(xd, pd_).cpu().numpy()[:, :n]
+    monkeypatch.setenv("FASTPROJECT_B200_ROW_STAGE", "off")
+    z_global = E.normalize_rows(xd).cpu().numpy()[:, :n]
+    w_global = E.compute_weights(xd, pd_).cpu().numpy()[:, :n]
+    monkeypatch.delenv("FASTPROJECT_B200_ROW_STAGE")
+    assert np.array_equal(z_staged, z_global)
+    assert np.array_equal(w_staged, w_global, equal_nan=True)
+    assert np.array_equal(z_staged, O.row_normalization(x))
+    with np.errstate(all="ignore"):
+        want = O.compute_weights(O.logistic_fnr, params, x, O.estimate_non_detection(x))
+    assert np.array_equal(np.isnan(w_staged), np.isnan(want))
+    np.testing.assert_allclose(w_staged, want, rtol=0, atol=WEIGHT_TOL, equal_nan=True)
+    # an odd pitch (rows not 16-byte aligned) falls back to the global-memory kernels by itself
+    odd = torch.zeros((g, n + 1 + n % 2), dtype=torch.float64, device="cuda")[:, :n]
+    odd.copy_(xd)
+    assert odd.stride(0) % 2 == 1
+    assert np.array_equal(E.normalize_rows(odd).cpu().numpy()[:, :n], z_staged)
+    assert np.array_equal(E.compute_weights(odd, pd_).cpu().numpy()[:, :n], w_staged, equal_nan=True)
+
+
 def test_compute_weights_midsize_vs_oracle_and_feeds_scoring(fp):
     """20 000 cells per gene, soft p_nd, device-resident output feeding calculate_sig_scores."""
     import torch
