@@ -697,6 +697,28 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
         if trace is not None:
             trace.append((what, time.perf_counter()))
 
+    if trace is not None:                      # who stalls the host: collector passes, pinned allocations
+        import gc
+        started = {}
+
+        def on_gc(phase, info):
+            if phase == "start":
+                started["t"] = time.perf_counter()
+            elif time.perf_counter() - started.get("t", 0) > 2e-3:
+                sys.stderr.write("e2e gc gen%d %.1f ms (%d collected)\n"
+                                 % (info["generation"], 1e3 * (time.perf_counter() - started["t"]), info["collected"]))
+        gc.callbacks.append(on_gc)
+        real_slot = E._pinned_slot
+
+        def traced_slot(nbytes):
+            n0, t0 = len(E._small_pool), time.perf_counter()
+            slot = real_slot(nbytes)
+            if len(E._small_pool) != n0:
+                sys.stderr.write("e2e new pinned slot of %d bytes: %.1f ms (pool %d)\n"
+                                 % (slot[0].numel(), 1e3 * (time.perf_counter() - t0), len(E._small_pool)))
+            return slot
+        E._pinned_slot = traced_slot
+
     def one_step(raw, nxt):
         stamp("begin")
         FP.prefetch(raw)
@@ -729,6 +751,12 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
     for it in range(warm):
         real, rnd, d2h = one_step(host[it % 2], host[(it + 1) % 2] if it + 1 < warm else None)
     E.clear_device_cache()
+    # the collector stays on, but what exists now (the interpreter's modules, the workload, the
+    # CPU checker's job: about a million container objects, 30-170 ms per full pass) is moved out
+    # of its generations, so a full pass inside the timed region walks only the steps' own objects
+    import gc
+    gc.collect()
+    gc.freeze()
     torch.cuda.synchronize()
     if dist_mode:
         dist.barrier()
@@ -737,6 +765,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
         real, rnd, d2h = one_step(host[it % 2], host[(it + 1) % 2] if it + 1 < steps else None)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    gc.unfreeze()
     if trace is not None:
         for (a, ta), (b, tb) in zip(trace[:-1], trace[1:]):
             if b != "begin":
@@ -760,7 +789,7 @@ def run_e2e(args, cfg, wl, precision, world=1, device=None):
             "api": "fastproject_b200.prefetch(raw) -> Transforms.compute_weights + NormalizationMethods."
                    "row_normalization on the device -> Signatures.calculate_sig_scores x2 -> Signatures."
                    "sigs_vs_projections(distributed=%s); pinned host input; steps back to back, the upload of "
-                   "the next step's matrix overlaps the current step%s"
+                   "the next step's matrix overlaps the current step; gc.freeze() before the timed loop%s"
                    % (dist_mode, "; one job: every rank uploads its 1/world of the gene rows over its own PCIe "
                       "link, makes weights and z-scores for them, and X / W are all-gathered over NVLink"
                       if dist_mode else "")}

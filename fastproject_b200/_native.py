@@ -80,6 +80,27 @@ def load():
     return lib
 
 
+_pack_ext = None
+
+
+def pack_ext():
+    """The CPython extension next to the shared library (csrc/pack_ext.c: signature dicts -> CSR
+    arrays).  Raises if it has not been built."""
+    global _pack_ext
+    if _pack_ext is None:
+        import glob
+        import importlib.util
+        found = sorted(glob.glob(os.path.join(os.path.dirname(LIB_PATH), "_fp_pack*.so")))
+        if not found:
+            raise NativeError("fastproject_b200: _fp_pack extension not found in %s -- run "
+                              "`python __graft_entry__.py`" % os.path.dirname(LIB_PATH))
+        spec = importlib.util.spec_from_file_location("_fp_pack", found[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _pack_ext = mod
+    return _pack_ext
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise NativeError on a non-zero code."""
     lib = load()

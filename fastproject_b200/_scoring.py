@@ -5,9 +5,6 @@
 ``ScoreBatch`` and its lazy host views."""
 from __future__ import annotations
 
-import itertools
-import operator
-
 import numpy as np
 import torch
 
@@ -64,87 +61,28 @@ def signature_rows(sig_dict, index):
     return rows, signs
 
 
-def _match_rows(flat_genes, n_entries, row_labels):
-    """Rows of the named genes (-1: not on the matrix) through the library's host-side hash
-    table (``fp_match_labels``); None when the labels are duplicated or are not plain strings
-    (the caller then takes the per-signature path)."""
-    from . import _native
-    try:
-        labels = "\0".join(row_labels).encode("utf-8")
-        queries = "\0".join(flat_genes).encode("utf-8")
-    except TypeError:
-        return None
-    rows = np.empty(n_entries, dtype=np.int32)
-    rc = _native.load().fp_match_labels(labels, len(labels), len(row_labels), queries, len(queries),
-                                        n_entries, rows.ctypes.data)
-    if rc != 0:
-        return None
-    return rows
-
-
-def _signs_of(dicts, n_entries):
-    """+1 for a dict value equal to 1 or 0, -1 for -1, 0 (= ignored) for anything else
-    (Signatures.py:750-753); None if the values are not numbers."""
-    kinds = set(itertools.chain.from_iterable(map(dict.values, dicts)))
-    try:
-        if kinds <= {1, 0}:                       # unsigned lists, every random background list
-            return np.ones(n_entries, dtype=np.int8)
-        flat_vals = list(itertools.chain.from_iterable(map(dict.values, dicts)))
-        if kinds <= {1, 0, -1}:
-            v = np.frombuffer(bytes(map((1).__add__, flat_vals)), dtype=np.uint8).astype(np.int8) - 1
-            return np.where(v == 0, 1, v).astype(np.int8)
-        vals = np.fromiter(flat_vals, dtype=np.float64, count=len(flat_vals))
-    except (TypeError, ValueError):
-        return None
-    return np.where((vals == 1) | (vals == 0), 1, np.where(vals == -1, -1, 0)).astype(np.int8)
-
-
 def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject=False):
     """list[Signature] -> (kept positions, sig_ptr, sig_gene, sig_sign, num_genes).
     Signatures with no matched gene, or fewer than ``min_signature_genes``, are
     rejected -- the reference raises ValueError for them
     (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676).
 
-    All signatures are matched in one pass: the gene names of the whole list go to the
-    library's host-side hash table as one NUL-separated blob (no Python object per gene), one
-    sort orders the entries by (signature, gene row); duplicated row labels and non-string
-    names take the per-signature path."""
-    if raise_on_reject or len(signatures) < 8:
-        return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
+    All signatures are packed in one call of the host extension (csrc/pack_ext.c): it walks the
+    sig_dicts, looks every gene up in the label -> row dict with the strings' cached hashes and
+    writes the CSR arrays directly.  Duplicated row labels, non-numeric dict values and
+    ``raise_on_reject`` take the per-signature path."""
+    index = gene_row_index(row_labels)
+    if raise_on_reject:
+        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+    from . import _native
     dicts = [sig.sig_dict for sig in signatures]
-    lengths = np.fromiter((len(d) for d in dicts), dtype=np.int64, count=len(dicts))
-    n_entries = int(lengths.sum())
-    rows = _match_rows(itertools.chain.from_iterable(dicts), n_entries, row_labels) if n_entries else \
-        np.zeros(0, dtype=np.int32)
-    signs = _signs_of(dicts, n_entries) if rows is not None else None
-    if rows is None or signs is None:
-        return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
-    rows = rows.astype(np.int64)
-    sig_id = np.repeat(np.arange(len(dicts), dtype=np.int64), lengths)
-    ok = (rows >= 0) & (signs != 0)
-    if not ok.all():
-        rows, signs, sig_id = rows[ok], signs[ok], sig_id[ok]
-    counts_all = np.bincount(sig_id, minlength=len(dicts)).astype(np.int64)
-    keep_sig = (counts_all > 0) & (counts_all >= min_signature_genes)
-    if not keep_sig.all():
-        entry_ok = keep_sig[sig_id]
-        rows, signs, sig_id = rows[entry_ok], signs[entry_ok], sig_id[entry_ok]
-    # by signature, ascending gene row inside: one sort of a combined key carrying the sign bit
-    # (32-bit keys sort about twice as fast; they hold 2 * signatures * genes < 2^31)
-    n_rows_total = len(row_labels)
-    key_t = np.int32 if 2 * len(dicts) * n_rows_total < 2 ** 31 else np.int64
-    key = ((sig_id * n_rows_total + rows) * 2 + (signs > 0)).astype(key_t)
-    key.sort()
-    signs = ((key & 1) * 2 - 1).astype(np.int8)
-    rows = (key >> 1) % n_rows_total
-    kept = np.nonzero(keep_sig)[0]
-    counts = counts_all[kept]
-    ptr = np.zeros(len(kept) + 1, dtype=np.int64)
-    np.cumsum(counts, out=ptr[1:])
-    if ptr[-1] >= 2 ** 31:
-        raise ValueError("signature membership table exceeds int32 indexing")
-    return ([int(k) for k in kept], ptr.astype(np.int32), rows.astype(np.int32),
-            signs.astype(np.int8), counts)
+    packed = _native.pack_ext().pack(dicts, index, float(min_signature_genes))
+    if packed is None:
+        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+    kept, ptr, rows, signs, counts = packed
+    return (np.frombuffer(kept, dtype=np.int64).tolist(), np.frombuffer(ptr, dtype=np.int32),
+            np.frombuffer(rows, dtype=np.int32), np.frombuffer(signs, dtype=np.int8),
+            np.frombuffer(counts, dtype=np.int64))
 
 
 def _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject=False):

@@ -1,0 +1,205 @@
+/* Signature -> CSR packing on the host, straight from the Python dicts.
+ *
+ * Replaces the per-signature loop of Signature.sig_indices
+ * (/root/reference/FastProject/Signatures.py:738-753) for a whole list of signatures at once:
+ * every (gene, value) item of every sig_dict is looked up in the gene -> row dict of the
+ * expression matrix (the strings' cached hashes: no re-hashing, no copies of the names) and
+ * written as (row, sign) into the CSR arrays the scoring kernel reads, rows ascending inside a
+ * signature.  A dict value equal to 1 or 0 counts as +1, equal to -1 as -1, anything else is
+ * ignored (:750-753); signatures with no matched gene or fewer than `min_genes` are rejected
+ * (SigScoreMethods.py:60-64).  Anything unusual -- duplicated row labels (list-valued index
+ * entries), values that are neither int nor float -- returns None and the caller takes the
+ * per-signature Python path.
+ *
+ * A CPython extension (not part of the C ABI of include/fastproject_b200.h): it walks Python
+ * objects.  fp_match_labels is the same matcher for callers that hold plain label buffers.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static int cmp_i64(const void *a, const void *b) {
+    const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+    return (x > y) - (x < y);
+}
+
+/* keys = row * 2 + (sign > 0), rows distinct and < n_rows: ascending.  Short lists by insertion;
+ * longer ones through a bitmap of the rows (set, then swept in order: O(n + n_rows / 64)) when
+ * that is cheaper than comparing. */
+static void sort_keys(int64_t *k, Py_ssize_t n, uint64_t *seen, uint64_t *positive, Py_ssize_t n_rows) {
+    if (n > 32 && seen && (n_rows >> 6) < 8 * n) {
+        Py_ssize_t lo = n_rows >> 6, hi = 0;
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            const int64_t row = k[i] >> 1;
+            const Py_ssize_t w = (Py_ssize_t)(row >> 6);
+            seen[w] |= 1ull << (row & 63);
+            if (k[i] & 1) positive[w] |= 1ull << (row & 63);
+            if (w < lo) lo = w;
+            if (w > hi) hi = w;
+        }
+        Py_ssize_t out = 0;
+        for (Py_ssize_t w = lo; w <= hi; ++w) {
+            uint64_t bits = seen[w];
+            const uint64_t pos = positive[w];
+            while (bits) {
+                const int b = __builtin_ctzll(bits);
+                bits &= bits - 1;
+                k[out++] = (((int64_t)w << 6) + b) * 2 + (int64_t)((pos >> b) & 1);
+            }
+            seen[w] = 0;
+            positive[w] = 0;
+        }
+        return;
+    }
+    if (n <= 48) {                                  /* the usual signature: insertion sort */
+        for (Py_ssize_t i = 1; i < n; ++i) {
+            const int64_t v = k[i];
+            Py_ssize_t j = i;
+            while (j > 0 && k[j - 1] > v) {
+                k[j] = k[j - 1];
+                --j;
+            }
+            k[j] = v;
+        }
+    } else {
+        qsort(k, (size_t)n, sizeof(int64_t), cmp_i64);
+    }
+}
+
+/* sign of a dict value: 1, -1, 0 (ignored); -2: not a plain number */
+static int sign_of(PyObject *v) {
+    if (PyLong_Check(v)) {
+        int overflow = 0;
+        const long x = PyLong_AsLongAndOverflow(v, &overflow);
+        if (overflow) return 0;
+        return (x == 1 || x == 0) ? 1 : (x == -1 ? -1 : 0);
+    }
+    if (PyFloat_Check(v)) {
+        const double x = PyFloat_AS_DOUBLE(v);
+        return (x == 1.0 || x == 0.0) ? 1 : (x == -1.0 ? -1 : 0);
+    }
+    return -2;
+}
+
+/* pack(dicts: list[dict], index: dict, min_genes: float)
+ *   -> None | (kept int64[], ptr int32[], rows int32[], signs int8[], counts int64[]) as bytearrays */
+static PyObject *pack(PyObject *self, PyObject *args) {
+    PyObject *dicts, *index;
+    double min_genes;
+    if (!PyArg_ParseTuple(args, "O!O!d", &PyList_Type, &dicts, &PyDict_Type, &index, &min_genes)) return NULL;
+    const Py_ssize_t n_sigs = PyList_GET_SIZE(dicts);
+    Py_ssize_t n_entries = 0, longest = 0;
+    for (Py_ssize_t s = 0; s < n_sigs; ++s) {
+        PyObject *d = PyList_GET_ITEM(dicts, s);
+        if (!PyDict_CheckExact(d)) Py_RETURN_NONE;
+        const Py_ssize_t n = PyDict_GET_SIZE(d);
+        n_entries += n;
+        if (n > longest) longest = n;
+    }
+    if (n_entries >= (Py_ssize_t)INT32_MAX) {
+        PyErr_SetString(PyExc_ValueError, "signature membership table exceeds int32 indexing");
+        return NULL;
+    }
+    int64_t *keys = (int64_t *)malloc(sizeof(int64_t) * (size_t)(longest + 1));
+    PyObject **items = (PyObject **)malloc(sizeof(PyObject *) * 2 * (size_t)(longest + 1));
+    const Py_ssize_t n_rows = PyDict_GET_SIZE(index);          /* rows are 0 .. n_rows - 1 when no label repeats */
+    uint64_t *seen = (uint64_t *)calloc((size_t)(n_rows / 64 + 1) * 2, sizeof(uint64_t));
+    uint64_t *positive = seen ? seen + (n_rows / 64 + 1) : NULL;
+    PyObject *b_kept = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int64_t) * n_sigs);
+    PyObject *b_ptr = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int32_t) * (n_sigs + 1));
+    PyObject *b_rows = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int32_t) * n_entries);
+    PyObject *b_signs = PyByteArray_FromStringAndSize(NULL, n_entries);
+    PyObject *b_counts = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int64_t) * n_sigs);
+    PyObject *result = NULL;
+    int unusual = 0;
+    if (!keys || !items || !seen || !b_kept || !b_ptr || !b_rows || !b_signs || !b_counts) {
+        PyErr_NoMemory();
+        goto done;
+    }
+    {
+        int64_t *kept = (int64_t *)PyByteArray_AS_STRING(b_kept);
+        int32_t *ptr = (int32_t *)PyByteArray_AS_STRING(b_ptr);
+        int32_t *rows = (int32_t *)PyByteArray_AS_STRING(b_rows);
+        int8_t *signs = (int8_t *)PyByteArray_AS_STRING(b_signs);
+        int64_t *counts = (int64_t *)PyByteArray_AS_STRING(b_counts);
+        Py_ssize_t n_kept = 0, fill = 0;
+        ptr[0] = 0;
+        for (Py_ssize_t s = 0; s < n_sigs && !unusual; ++s) {
+            PyObject *d = PyList_GET_ITEM(dicts, s), *gene, *value;
+            Py_ssize_t pos = 0, n = 0;
+            long max_row = 0;
+            /* two passes over the items: the first only collects them and asks for the cache
+             * lines of the name objects (their cached hashes), so that the lookups of the second
+             * pass do not each wait for memory */
+            Py_ssize_t n_items = 0;
+            while (PyDict_Next(d, &pos, &gene, &value)) {
+                __builtin_prefetch(gene);
+                items[2 * n_items] = gene;
+                items[2 * n_items + 1] = value;
+                ++n_items;
+            }
+            for (Py_ssize_t it = 0; it < n_items; ++it) {
+                gene = items[2 * it];
+                value = items[2 * it + 1];
+                PyObject *hit = PyDict_GetItemWithError(index, gene);       /* borrowed */
+                if (!hit) {
+                    if (PyErr_Occurred()) goto done;                          /* unhashable name */
+                    continue;
+                }
+                if (!PyLong_CheckExact(hit)) {                                /* duplicated label */
+                    unusual = 1;
+                    break;
+                }
+                const int sg = sign_of(value);
+                if (sg == -2) {
+                    unusual = 1;
+                    break;
+                }
+                if (sg == 0) continue;
+                const long row = PyLong_AsLong(hit);
+                if (row > max_row) max_row = row;
+                keys[n++] = (int64_t)row * 2 + (sg > 0);
+            }
+            if (unusual) break;
+            if (n == 0 || (double)n < min_genes) continue;
+            sort_keys(keys, n, max_row < n_rows ? seen : NULL, positive, n_rows);
+            for (Py_ssize_t i = 0; i < n; ++i) {
+                rows[fill + i] = (int32_t)(keys[i] >> 1);
+                signs[fill + i] = (keys[i] & 1) ? 1 : -1;
+            }
+            fill += n;
+            kept[n_kept] = s;
+            counts[n_kept] = n;
+            ptr[++n_kept] = (int32_t)fill;
+        }
+        if (unusual) goto done;
+        if (PyByteArray_Resize(b_kept, (Py_ssize_t)sizeof(int64_t) * n_kept) < 0 ||
+            PyByteArray_Resize(b_ptr, (Py_ssize_t)sizeof(int32_t) * (n_kept + 1)) < 0 ||
+            PyByteArray_Resize(b_rows, (Py_ssize_t)sizeof(int32_t) * fill) < 0 ||
+            PyByteArray_Resize(b_signs, fill) < 0 ||
+            PyByteArray_Resize(b_counts, (Py_ssize_t)sizeof(int64_t) * n_kept) < 0)
+            goto done;
+        result = PyTuple_Pack(5, b_kept, b_ptr, b_rows, b_signs, b_counts);
+    }
+done:
+    free(keys);
+    free(items);
+    free(seen);
+    Py_XDECREF(b_kept);
+    Py_XDECREF(b_ptr);
+    Py_XDECREF(b_rows);
+    Py_XDECREF(b_signs);
+    Py_XDECREF(b_counts);
+    if (!result && !PyErr_Occurred()) Py_RETURN_NONE;                         /* unusual input */
+    return result;
+}
+
+static PyMethodDef methods[] = {
+    {"pack", pack, METH_VARARGS, "pack(dicts, index, min_genes) -> None | (kept, ptr, rows, signs, counts) bytearrays"},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_fp_pack", "signature -> CSR packing", -1, methods};
+
+PyMODINIT_FUNC PyInit__fp_pack(void) { return PyModule_Create(&module); }

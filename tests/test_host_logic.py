@@ -7,6 +7,50 @@ import pytest
 
 from fastproject_b200 import Signatures as S
 from fastproject_b200 import _scoring
+
+
+def test_packer_extension_long_lists_odd_values_and_fallbacks():
+    """csrc/pack_ext.c against the per-signature path: lists long enough for the bitmap ordering
+    (> 32 genes), signed entries, float / bool / numpy values, ignored values, names that are not
+    on the matrix, rejected signatures, an empty list; inputs it declines (numpy integers as
+    values, duplicated labels, dict subclasses) must come back as None, not as a wrong table."""
+    from fastproject_b200 import _native
+    ext = _native.pack_ext()
+
+    class Sig(object):
+        def __init__(self, d):
+            self.sig_dict = d
+    rng = np.random.RandomState(11)
+    genes = ["gene_%d" % i for i in range(5000)]
+    values = [1, -1, 0, 1.0, -1.0, 0.0, True, 2, 0.5, np.float64(-1.0), -7, 10 ** 30]
+    sigs = []
+    for size in (1, 2, 5, 31, 32, 33, 48, 49, 100, 640, 3000):
+        d = dict((genes[j], values[int(rng.randint(len(values)))]) for j in rng.choice(5000, size, replace=False))
+        d["not_on_the_matrix_%d" % size] = 1
+        sigs.append(Sig(d))
+    sigs.append(Sig({}))
+    sigs.append(Sig({"nowhere": 1}))
+    index = _scoring.gene_row_index(genes)
+    for min_genes in (0, 3, 40, 1e99):
+        fast = _scoring.pack_signatures(sigs, genes, min_genes)
+        slow = _scoring._pack_signatures_slow(sigs, index, min_genes)
+        assert fast[0] == slow[0]
+        for a, b in zip(fast[1:], slow[1:]):
+            assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
+        assert ext.pack([s.sig_dict for s in sigs], index, float(min_genes)) is not None
+    assert [len(np.frombuffer(b, dtype=np.uint8)) for b in ext.pack([], index, 0.0)] == [0, 4, 0, 0, 0]
+    assert ext.pack([{genes[0]: np.int64(1)}], index, 0.0) is None
+    assert ext.pack([{genes[0]: "1"}], index, 0.0) is None
+    assert ext.pack([{genes[0]: 1}], _scoring.gene_row_index(genes[:10] + genes[:10]), 0.0) is None
+    import collections
+    assert ext.pack([collections.OrderedDict({genes[0]: 1})], index, 0.0) is None
+    # ... and the public packer still answers for all of them
+    odd = [Sig({genes[0]: np.int64(1), genes[7]: np.int64(-1)}), Sig(collections.OrderedDict({genes[3]: 1}))] * 5
+    fast = _scoring.pack_signatures(odd, genes, 0)
+    slow = _scoring._pack_signatures_slow(odd, index, 0)
+    assert fast[0] == slow[0] and all(np.array_equal(a, b) for a, b in zip(fast[1:], slow[1:]))
+
+
 from oracle import fp_oracle as O
 from tests import _golden as G
 
