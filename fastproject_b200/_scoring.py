@@ -68,21 +68,42 @@ def pack_signatures(signatures, row_labels, min_signature_genes, raise_on_reject
     (SigScoreMethods.py:60-64) and calculate_sig_scores drops them (:672-676).
 
     All signatures are packed in one call of the host extension (csrc/pack_ext.c): it walks the
-    sig_dicts, looks every gene up in the label -> row dict with the strings' cached hashes and
-    writes the CSR arrays directly.  Duplicated row labels, non-numeric dict values and
-    ``raise_on_reject`` take the per-signature path."""
-    index = gene_row_index(row_labels)
-    if raise_on_reject:
-        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
-    from . import _native
-    dicts = [sig.sig_dict for sig in signatures]
-    packed = _native.pack_ext().pack(dicts, index, float(min_signature_genes))
+    sig_dicts, looks every gene up in a table of the row labels (the strings' cached hashes) and
+    writes the CSR arrays directly.  Duplicated or non-string row labels, non-numeric dict values
+    and ``raise_on_reject`` take the per-signature path."""
+    table = None if raise_on_reject else _label_table(row_labels)
+    packed = None
+    if table is not None:
+        from . import _native
+        packed = _native.pack_ext().pack([sig.sig_dict for sig in signatures], table, float(min_signature_genes))
     if packed is None:
-        return _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject)
+        return _pack_signatures_slow(signatures, gene_row_index(row_labels), min_signature_genes, raise_on_reject)
     kept, ptr, rows, signs, counts = packed
     return (np.frombuffer(kept, dtype=np.int64).tolist(), np.frombuffer(ptr, dtype=np.int32),
             np.frombuffer(rows, dtype=np.int32), np.frombuffer(signs, dtype=np.int8),
             np.frombuffer(counts, dtype=np.int64))
+
+
+_table_cache = []        # [(copy of the label list, table or None)], most recent first
+
+
+def _label_table(row_labels):
+    """The extension's label table of ``row_labels``; the last few are kept, and one is reused only
+    for a list that compares equal to the copy it was built from (a list comparison by identity
+    of the elements: microseconds) -- calculate_sig_scores is called twice per data set (real and
+    background signatures) with the same labels."""
+    if not isinstance(row_labels, list):
+        row_labels = list(row_labels)
+    for pos, (labels, table) in enumerate(_table_cache):
+        if len(labels) == len(row_labels) and labels == row_labels:
+            if pos:
+                _table_cache.insert(0, _table_cache.pop(pos))
+            return table
+    from . import _native
+    table = _native.pack_ext().label_table(row_labels)
+    _table_cache.insert(0, (list(row_labels), table))
+    del _table_cache[3:]
+    return table
 
 
 def _pack_signatures_slow(signatures, index, min_signature_genes, raise_on_reject=False):

@@ -2,13 +2,14 @@
  *
  * Replaces the per-signature loop of Signature.sig_indices
  * (/root/reference/FastProject/Signatures.py:738-753) for a whole list of signatures at once:
- * every (gene, value) item of every sig_dict is looked up in the gene -> row dict of the
- * expression matrix (the strings' cached hashes: no re-hashing, no copies of the names) and
+ * every (gene, value) item of every sig_dict is looked up in a table of the row labels of the
+ * expression matrix (open addressing on the strings' cached hashes, hit by object identity or by
+ * string equality: no re-hashing, no copies of the names, two cache lines per lookup) and
  * written as (row, sign) into the CSR arrays the scoring kernel reads, rows ascending inside a
  * signature.  A dict value equal to 1 or 0 counts as +1, equal to -1 as -1, anything else is
  * ignored (:750-753); signatures with no matched gene or fewer than `min_genes` are rejected
- * (SigScoreMethods.py:60-64).  Anything unusual -- duplicated row labels (list-valued index
- * entries), values that are neither int nor float -- returns None and the caller takes the
+ * (SigScoreMethods.py:60-64).  Anything unusual -- duplicated or non-string row labels (no table
+ * is built), values that are neither int nor float -- returns None and the caller takes the
  * per-signature Python path.
  *
  * A CPython extension (not part of the C ABI of include/fastproject_b200.h): it walks Python
@@ -68,6 +69,91 @@ static void sort_keys(int64_t *k, Py_ssize_t n, uint64_t *seen, uint64_t *positi
     }
 }
 
+/* ---- label table ------------------------------------------------------------------------- */
+typedef struct {
+    PyObject *key;          /* strong reference; NULL = empty slot */
+    Py_hash_t hash;
+    int64_t row;
+} Slot;
+
+typedef struct {
+    Slot *slots;
+    size_t mask;
+    Py_ssize_t n_rows;
+} Table;
+
+static void table_free(PyObject *capsule) {
+    Table *t = (Table *)PyCapsule_GetPointer(capsule, "fp_label_table");
+    if (!t) return;
+    if (t->slots) {
+        for (size_t i = 0; i <= t->mask; ++i) Py_XDECREF(t->slots[i].key);
+        free(t->slots);
+    }
+    free(t);
+}
+
+/* row of a name, -1: not on the matrix, -2: error set */
+static inline int64_t table_find(const Table *t, PyObject *name) {
+    if (!PyUnicode_CheckExact(name)) {
+        /* other hashables can equal a str only through their own __eq__ (str subclasses, ...):
+         * the dict-based path decides */
+        return -3;
+    }
+    Py_hash_t h = ((PyASCIIObject *)name)->hash;
+    if (h == -1) {
+        h = PyObject_Hash(name);
+        if (h == -1) return -2;
+    }
+    for (size_t i = (size_t)h & t->mask;; i = (i + 1) & t->mask) {
+        const Slot *s = &t->slots[i];
+        if (!s->key) return -1;
+        if (s->key == name) return s->row;
+        if (s->hash == h && PyUnicode_Compare(s->key, name) == 0) return s->row;
+    }
+}
+
+/* label_table(labels: list[str]) -> capsule | None (duplicated or non-str labels) */
+static PyObject *label_table(PyObject *self, PyObject *arg) {
+    if (!PyList_CheckExact(arg)) Py_RETURN_NONE;
+    const Py_ssize_t n = PyList_GET_SIZE(arg);
+    size_t cap = 16;
+    while (cap < (size_t)n * 2 + 2) cap <<= 1;
+    Table *t = (Table *)calloc(1, sizeof(Table));
+    if (!t) return PyErr_NoMemory();
+    t->slots = (Slot *)calloc(cap, sizeof(Slot));
+    t->mask = cap - 1;
+    t->n_rows = n;
+    PyObject *capsule = t->slots ? PyCapsule_New(t, "fp_label_table", table_free) : NULL;
+    if (!capsule) {
+        free(t->slots);
+        free(t);
+        return PyErr_NoMemory();
+    }
+    for (Py_ssize_t r = 0; r < n; ++r) {
+        PyObject *name = PyList_GET_ITEM(arg, r);
+        if (!PyUnicode_CheckExact(name)) goto decline;
+        const Py_hash_t h = PyObject_Hash(name);
+        if (h == -1) {
+            Py_DECREF(capsule);
+            return NULL;
+        }
+        size_t i = (size_t)h & t->mask;
+        for (;; i = (i + 1) & t->mask) {
+            Slot *s = &t->slots[i];
+            if (!s->key) break;
+            if (s->key == name || (s->hash == h && PyUnicode_Compare(s->key, name) == 0)) goto decline;   /* duplicate */
+        }
+        Py_INCREF(name);
+        t->slots[i].key = name;
+        t->slots[i].hash = h;
+        t->slots[i].row = r;
+    }
+    return capsule;
+decline:
+    Py_DECREF(capsule);
+    Py_RETURN_NONE;
+}
+
 /* sign of a dict value: 1, -1, 0 (ignored); -2: not a plain number */
 static int sign_of(PyObject *v) {
     if (PyLong_Check(v)) {
@@ -83,12 +169,14 @@ static int sign_of(PyObject *v) {
     return -2;
 }
 
-/* pack(dicts: list[dict], index: dict, min_genes: float)
+/* pack(dicts: list[dict], table: capsule of label_table(), min_genes: float)
  *   -> None | (kept int64[], ptr int32[], rows int32[], signs int8[], counts int64[]) as bytearrays */
 static PyObject *pack(PyObject *self, PyObject *args) {
-    PyObject *dicts, *index;
+    PyObject *dicts, *capsule;
     double min_genes;
-    if (!PyArg_ParseTuple(args, "O!O!d", &PyList_Type, &dicts, &PyDict_Type, &index, &min_genes)) return NULL;
+    if (!PyArg_ParseTuple(args, "O!Od", &PyList_Type, &dicts, &capsule, &min_genes)) return NULL;
+    const Table *table = (const Table *)PyCapsule_GetPointer(capsule, "fp_label_table");
+    if (!table) return NULL;
     const Py_ssize_t n_sigs = PyList_GET_SIZE(dicts);
     Py_ssize_t n_entries = 0, longest = 0;
     for (Py_ssize_t s = 0; s < n_sigs; ++s) {
@@ -104,7 +192,7 @@ static PyObject *pack(PyObject *self, PyObject *args) {
     }
     int64_t *keys = (int64_t *)malloc(sizeof(int64_t) * (size_t)(longest + 1));
     PyObject **items = (PyObject **)malloc(sizeof(PyObject *) * 2 * (size_t)(longest + 1));
-    const Py_ssize_t n_rows = PyDict_GET_SIZE(index);          /* rows are 0 .. n_rows - 1 when no label repeats */
+    const Py_ssize_t n_rows = table->n_rows;
     uint64_t *seen = (uint64_t *)calloc((size_t)(n_rows / 64 + 1) * 2, sizeof(uint64_t));
     uint64_t *positive = seen ? seen + (n_rows / 64 + 1) : NULL;
     PyObject *b_kept = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int64_t) * n_sigs);
@@ -129,7 +217,6 @@ static PyObject *pack(PyObject *self, PyObject *args) {
         for (Py_ssize_t s = 0; s < n_sigs && !unusual; ++s) {
             PyObject *d = PyList_GET_ITEM(dicts, s), *gene, *value;
             Py_ssize_t pos = 0, n = 0;
-            long max_row = 0;
             /* two passes over the items: the first only collects them and asks for the cache
              * lines of the name objects (their cached hashes), so that the lookups of the second
              * pass do not each wait for memory */
@@ -143,14 +230,14 @@ static PyObject *pack(PyObject *self, PyObject *args) {
             for (Py_ssize_t it = 0; it < n_items; ++it) {
                 gene = items[2 * it];
                 value = items[2 * it + 1];
-                PyObject *hit = PyDict_GetItemWithError(index, gene);       /* borrowed */
-                if (!hit) {
-                    if (PyErr_Occurred()) goto done;                          /* unhashable name */
+                const int64_t row = table_find(table, gene);
+                if (row < 0) {
+                    if (row == -2) goto done;
+                    if (row == -3) {                                          /* a name that is not a plain str */
+                        unusual = 1;
+                        break;
+                    }
                     continue;
-                }
-                if (!PyLong_CheckExact(hit)) {                                /* duplicated label */
-                    unusual = 1;
-                    break;
                 }
                 const int sg = sign_of(value);
                 if (sg == -2) {
@@ -158,13 +245,11 @@ static PyObject *pack(PyObject *self, PyObject *args) {
                     break;
                 }
                 if (sg == 0) continue;
-                const long row = PyLong_AsLong(hit);
-                if (row > max_row) max_row = row;
-                keys[n++] = (int64_t)row * 2 + (sg > 0);
+                keys[n++] = row * 2 + (sg > 0);
             }
             if (unusual) break;
             if (n == 0 || (double)n < min_genes) continue;
-            sort_keys(keys, n, max_row < n_rows ? seen : NULL, positive, n_rows);
+            sort_keys(keys, n, seen, positive, n_rows);
             for (Py_ssize_t i = 0; i < n; ++i) {
                 rows[fill + i] = (int32_t)(keys[i] >> 1);
                 signs[fill + i] = (keys[i] & 1) ? 1 : -1;
@@ -197,7 +282,8 @@ done:
 }
 
 static PyMethodDef methods[] = {
-    {"pack", pack, METH_VARARGS, "pack(dicts, index, min_genes) -> None | (kept, ptr, rows, signs, counts) bytearrays"},
+    {"label_table", label_table, METH_O, "label_table(labels) -> capsule | None (duplicated / non-str labels)"},
+    {"pack", pack, METH_VARARGS, "pack(dicts, table, min_genes) -> None | (kept, ptr, rows, signs, counts) bytearrays"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_fp_pack", "signature -> CSR packing", -1, methods};

@@ -31,19 +31,37 @@ def test_packer_extension_long_lists_odd_values_and_fallbacks():
     sigs.append(Sig({}))
     sigs.append(Sig({"nowhere": 1}))
     index = _scoring.gene_row_index(genes)
+    table = ext.label_table(genes)
     for min_genes in (0, 3, 40, 1e99):
         fast = _scoring.pack_signatures(sigs, genes, min_genes)
         slow = _scoring._pack_signatures_slow(sigs, index, min_genes)
         assert fast[0] == slow[0]
         for a, b in zip(fast[1:], slow[1:]):
             assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
-        assert ext.pack([s.sig_dict for s in sigs], index, float(min_genes)) is not None
-    assert [len(np.frombuffer(b, dtype=np.uint8)) for b in ext.pack([], index, 0.0)] == [0, 4, 0, 0, 0]
-    assert ext.pack([{genes[0]: np.int64(1)}], index, 0.0) is None
-    assert ext.pack([{genes[0]: "1"}], index, 0.0) is None
-    assert ext.pack([{genes[0]: 1}], _scoring.gene_row_index(genes[:10] + genes[:10]), 0.0) is None
+        assert ext.pack([s.sig_dict for s in sigs], table, float(min_genes)) is not None
+    assert [len(np.frombuffer(b, dtype=np.uint8)) for b in ext.pack([], table, 0.0)] == [0, 4, 0, 0, 0]
+    assert ext.pack([{genes[0]: np.int64(1)}], table, 0.0) is None
+    assert ext.pack([{genes[0]: "1"}], table, 0.0) is None
+    assert ext.pack([{genes[0]: 1, 17: 1}], table, 0.0) is None         # a name that is not a str
+    assert ext.label_table(genes[:10] + genes[:10]) is None             # duplicated labels: no table
+    assert ext.label_table(genes[:10] + [3]) is None                    # labels that are not str
+    assert ext.label_table(tuple(genes)) is None
+    with pytest.raises(ValueError):
+        ext.pack([{genes[0]: 1}], index, 0.0)                           # not a table
     import collections
-    assert ext.pack([collections.OrderedDict({genes[0]: 1})], index, 0.0) is None
+    assert ext.pack([collections.OrderedDict({genes[0]: 1})], table, 0.0) is None
+    # equal names held by OTHER str objects (signatures read from a file) match by content
+    copies = dict(("gene_" + str(i), 1) for i in (5, 17, 4999))
+    got = ext.pack([copies], table, 0.0)
+    assert list(np.frombuffer(got[2], dtype=np.int32)) == [5, 17, 4999]
+    # the cached table follows the CONTENT of the label list, not the object
+    labels = list(genes)
+    a = _scoring.pack_signatures(sigs, labels, 0)
+    labels[0], labels[1] = labels[1], labels[0]
+    b = _scoring.pack_signatures(sigs, labels, 0)
+    want = _scoring._pack_signatures_slow(sigs, _scoring.gene_row_index(labels), 0)
+    assert all(np.array_equal(x, y) for x, y in zip(b[1:], want[1:]))
+    assert not all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
     # ... and the public packer still answers for all of them
     odd = [Sig({genes[0]: np.int64(1), genes[7]: np.int64(-1)}), Sig(collections.OrderedDict({genes[3]: 1}))] * 5
     fast = _scoring.pack_signatures(odd, genes, 0)
