@@ -17,9 +17,12 @@
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#define MATCH_THREADS 4
 
 static int cmp_i64(const void *a, const void *b) {
     const int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
@@ -92,18 +95,15 @@ static void table_free(PyObject *capsule) {
     free(t);
 }
 
-/* row of a name, -1: not on the matrix, -2: error set */
+/* row of a name, -1: not on the matrix, -3: not for this table (read-only: safe without the GIL) */
 static inline int64_t table_find(const Table *t, PyObject *name) {
     if (!PyUnicode_CheckExact(name)) {
         /* other hashables can equal a str only through their own __eq__ (str subclasses, ...):
          * the dict-based path decides */
         return -3;
     }
-    Py_hash_t h = ((PyASCIIObject *)name)->hash;
-    if (h == -1) {
-        h = PyObject_Hash(name);
-        if (h == -1) return -2;
-    }
+    const Py_hash_t h = ((PyASCIIObject *)name)->hash;
+    if (h == -1) return -3;      /* not cached: cannot happen for a dict key; the Python path decides */
     for (size_t i = (size_t)h & t->mask;; i = (i + 1) & t->mask) {
         const Slot *s = &t->slots[i];
         if (!s->key) return -1;
@@ -169,6 +169,73 @@ static int sign_of(PyObject *v) {
     return -2;
 }
 
+/* ---- matching: a few threads, read-only --------------------------------------------------
+ * The caller holds the GIL for the whole call, so no Python code can change the dicts meanwhile;
+ * the workers only READ Python objects (PyDict_Next, cached str hashes, int / float payloads):
+ * no reference counts, no allocation, no error state.  Whatever would need more than that (a
+ * name whose hash is not cached, a value that is not a plain number) marks the job "unusual"
+ * and the caller takes the Python path. */
+typedef struct {
+    PyObject *dicts;
+    const Table *table;
+    const Py_ssize_t *offset;     /* first slot of signature s in keys (prefix sums of the dict sizes) */
+    int64_t *keys;                /* matched row * 2 + (sign > 0), ascending inside a signature */
+    int32_t *n_matched;           /* per signature */
+    Py_ssize_t n_sigs, longest;
+    int n_threads;
+    volatile int unusual;
+} Job;
+
+typedef struct {
+    Job *job;
+    int tid;
+} Worker;
+
+static void *match_worker(void *arg) {
+    Worker *w = (Worker *)arg;
+    Job *job = w->job;
+    const Table *table = job->table;
+    const Py_ssize_t n_rows = table->n_rows;
+    PyObject **items = (PyObject **)malloc(sizeof(PyObject *) * 2 * (size_t)(job->longest + 1));
+    uint64_t *seen = (uint64_t *)calloc((size_t)(n_rows / 64 + 1) * 2, sizeof(uint64_t));
+    uint64_t *positive = seen ? seen + (n_rows / 64 + 1) : NULL;
+    if (!items || !seen) job->unusual = 1;
+    for (Py_ssize_t s = w->tid; s < job->n_sigs && !job->unusual; s += job->n_threads) {
+        PyObject *d = PyList_GET_ITEM(job->dicts, s), *gene, *value;
+        int64_t *keys = job->keys + job->offset[s];
+        Py_ssize_t pos = 0, n = 0, n_items = 0;
+        /* two passes over the items: the first only collects them and asks for the cache lines
+         * of the name objects (their cached hashes) */
+        while (PyDict_Next(d, &pos, &gene, &value)) {
+            __builtin_prefetch(gene);
+            items[2 * n_items] = gene;
+            items[2 * n_items + 1] = value;
+            ++n_items;
+        }
+        for (Py_ssize_t it = 0; it < n_items; ++it) {
+            const int64_t row = table_find(table, items[2 * it]);
+            if (row < 0) {
+                if (row == -1) continue;                 /* not on the matrix */
+                job->unusual = 1;                        /* not a plain str / hash not cached */
+                break;
+            }
+            const int sg = sign_of(items[2 * it + 1]);
+            if (sg == -2) {
+                job->unusual = 1;
+                break;
+            }
+            if (sg == 0) continue;
+            keys[n++] = row * 2 + (sg > 0);
+        }
+        if (job->unusual) break;
+        sort_keys(keys, n, seen, positive, n_rows);
+        job->n_matched[s] = (int32_t)n;
+    }
+    free(items);
+    free(seen);
+    return NULL;
+}
+
 /* pack(dicts: list[dict], table: capsule of label_table(), min_genes: float)
  *   -> None | (kept int64[], ptr int32[], rows int32[], signs int8[], counts int64[]) as bytearrays */
 static PyObject *pack(PyObject *self, PyObject *args) {
@@ -178,35 +245,65 @@ static PyObject *pack(PyObject *self, PyObject *args) {
     const Table *table = (const Table *)PyCapsule_GetPointer(capsule, "fp_label_table");
     if (!table) return NULL;
     const Py_ssize_t n_sigs = PyList_GET_SIZE(dicts);
+    Py_ssize_t *offset = (Py_ssize_t *)malloc(sizeof(Py_ssize_t) * (size_t)(n_sigs + 1));
+    if (!offset) return PyErr_NoMemory();
     Py_ssize_t n_entries = 0, longest = 0;
     for (Py_ssize_t s = 0; s < n_sigs; ++s) {
         PyObject *d = PyList_GET_ITEM(dicts, s);
-        if (!PyDict_CheckExact(d)) Py_RETURN_NONE;
+        if (!PyDict_CheckExact(d)) {
+            free(offset);
+            Py_RETURN_NONE;
+        }
         const Py_ssize_t n = PyDict_GET_SIZE(d);
+        offset[s] = n_entries;
         n_entries += n;
         if (n > longest) longest = n;
     }
+    offset[n_sigs] = n_entries;
     if (n_entries >= (Py_ssize_t)INT32_MAX) {
+        free(offset);
         PyErr_SetString(PyExc_ValueError, "signature membership table exceeds int32 indexing");
         return NULL;
     }
-    int64_t *keys = (int64_t *)malloc(sizeof(int64_t) * (size_t)(longest + 1));
-    PyObject **items = (PyObject **)malloc(sizeof(PyObject *) * 2 * (size_t)(longest + 1));
-    const Py_ssize_t n_rows = table->n_rows;
-    uint64_t *seen = (uint64_t *)calloc((size_t)(n_rows / 64 + 1) * 2, sizeof(uint64_t));
-    uint64_t *positive = seen ? seen + (n_rows / 64 + 1) : NULL;
+    Job job;
+    job.dicts = dicts;
+    job.table = table;
+    job.offset = offset;
+    job.keys = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_entries + 1));
+    job.n_matched = (int32_t *)calloc((size_t)(n_sigs + 1), sizeof(int32_t));
+    job.n_sigs = n_sigs;
+    job.longest = longest;
+    job.n_threads = n_entries >= 16384 ? MATCH_THREADS : 1;
+    job.unusual = 0;
     PyObject *b_kept = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int64_t) * n_sigs);
     PyObject *b_ptr = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int32_t) * (n_sigs + 1));
     PyObject *b_rows = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int32_t) * n_entries);
     PyObject *b_signs = PyByteArray_FromStringAndSize(NULL, n_entries);
     PyObject *b_counts = PyByteArray_FromStringAndSize(NULL, (Py_ssize_t)sizeof(int64_t) * n_sigs);
     PyObject *result = NULL;
-    int unusual = 0;
-    if (!keys || !items || !seen || !b_kept || !b_ptr || !b_rows || !b_signs || !b_counts) {
+    if (!job.keys || !job.n_matched || !b_kept || !b_ptr || !b_rows || !b_signs || !b_counts) {
         PyErr_NoMemory();
         goto done;
     }
     {
+        Worker workers[MATCH_THREADS];
+        pthread_t threads[MATCH_THREADS];
+        int started[MATCH_THREADS] = {0};
+        for (int t = 0; t < job.n_threads; ++t) {
+            workers[t].job = &job;
+            workers[t].tid = t;
+        }
+        for (int t = 1; t < job.n_threads; ++t)
+            started[t] = pthread_create(&threads[t], NULL, match_worker, &workers[t]) == 0;
+        match_worker(&workers[0]);
+        for (int t = 1; t < job.n_threads; ++t) {
+            if (started[t]) {
+                pthread_join(threads[t], NULL);
+            } else {
+                match_worker(&workers[t]);               /* no thread to be had: do its share here */
+            }
+        }
+        if (job.unusual) goto done;
         int64_t *kept = (int64_t *)PyByteArray_AS_STRING(b_kept);
         int32_t *ptr = (int32_t *)PyByteArray_AS_STRING(b_ptr);
         int32_t *rows = (int32_t *)PyByteArray_AS_STRING(b_rows);
@@ -214,42 +311,10 @@ static PyObject *pack(PyObject *self, PyObject *args) {
         int64_t *counts = (int64_t *)PyByteArray_AS_STRING(b_counts);
         Py_ssize_t n_kept = 0, fill = 0;
         ptr[0] = 0;
-        for (Py_ssize_t s = 0; s < n_sigs && !unusual; ++s) {
-            PyObject *d = PyList_GET_ITEM(dicts, s), *gene, *value;
-            Py_ssize_t pos = 0, n = 0;
-            /* two passes over the items: the first only collects them and asks for the cache
-             * lines of the name objects (their cached hashes), so that the lookups of the second
-             * pass do not each wait for memory */
-            Py_ssize_t n_items = 0;
-            while (PyDict_Next(d, &pos, &gene, &value)) {
-                __builtin_prefetch(gene);
-                items[2 * n_items] = gene;
-                items[2 * n_items + 1] = value;
-                ++n_items;
-            }
-            for (Py_ssize_t it = 0; it < n_items; ++it) {
-                gene = items[2 * it];
-                value = items[2 * it + 1];
-                const int64_t row = table_find(table, gene);
-                if (row < 0) {
-                    if (row == -2) goto done;
-                    if (row == -3) {                                          /* a name that is not a plain str */
-                        unusual = 1;
-                        break;
-                    }
-                    continue;
-                }
-                const int sg = sign_of(value);
-                if (sg == -2) {
-                    unusual = 1;
-                    break;
-                }
-                if (sg == 0) continue;
-                keys[n++] = row * 2 + (sg > 0);
-            }
-            if (unusual) break;
+        for (Py_ssize_t s = 0; s < n_sigs; ++s) {
+            const Py_ssize_t n = job.n_matched[s];
             if (n == 0 || (double)n < min_genes) continue;
-            sort_keys(keys, n, seen, positive, n_rows);
+            const int64_t *keys = job.keys + offset[s];
             for (Py_ssize_t i = 0; i < n; ++i) {
                 rows[fill + i] = (int32_t)(keys[i] >> 1);
                 signs[fill + i] = (keys[i] & 1) ? 1 : -1;
@@ -259,7 +324,6 @@ static PyObject *pack(PyObject *self, PyObject *args) {
             counts[n_kept] = n;
             ptr[++n_kept] = (int32_t)fill;
         }
-        if (unusual) goto done;
         if (PyByteArray_Resize(b_kept, (Py_ssize_t)sizeof(int64_t) * n_kept) < 0 ||
             PyByteArray_Resize(b_ptr, (Py_ssize_t)sizeof(int32_t) * (n_kept + 1)) < 0 ||
             PyByteArray_Resize(b_rows, (Py_ssize_t)sizeof(int32_t) * fill) < 0 ||
@@ -269,9 +333,9 @@ static PyObject *pack(PyObject *self, PyObject *args) {
         result = PyTuple_Pack(5, b_kept, b_ptr, b_rows, b_signs, b_counts);
     }
 done:
-    free(keys);
-    free(items);
-    free(seen);
+    free(offset);
+    free(job.keys);
+    free(job.n_matched);
     Py_XDECREF(b_kept);
     Py_XDECREF(b_ptr);
     Py_XDECREF(b_rows);
