@@ -84,6 +84,18 @@ def calculate_sig_scores(data, signatures, method='weighted_avg',
     return sig_scores_dict
 
 
+def prefetch_scores(sig_scores_dict):
+    """Extension: start copying the scores of a ``calculate_sig_scores`` result to the host now
+    (asynchronously, on a side stream) instead of at the first read of a ``.scores`` -- the copy
+    then runs beside ``sigs_vs_projections``.  In a multi-GPU job it covers this rank's rows."""
+    seen = set()
+    for ss in sig_scores_dict.values():
+        batch = getattr(ss, "_batch", None)
+        if batch is not None and id(batch) not in seen:
+            seen.add(id(batch))
+            batch.prefetch_host()
+
+
 def generate_random_sigs(features, signed, sizes=None, num_per_size=3000):
     """Signatures.py:684-728.  Stays on the host and consumes the same two
     global RNG streams in the same order (``random.sample`` then

@@ -157,6 +157,26 @@ def to_device_replicated(arr):
 
 _PINNED_CHUNK = 32 << 20
 _pinned = []
+_d2h_stream = None
+
+
+def to_host_async(dev_tensor):
+    """Start the copy of a CUDA float64 matrix into a new pinned host tensor on a side stream
+    (it waits for what the current stream has queued so far, then runs beside whatever comes
+    next).  Returns (host tensor, event): the host tensor is valid after ``event.synchronize()``."""
+    global _d2h_stream
+    if _d2h_stream is None:
+        _d2h_stream = torch.cuda.Stream(device=dev_tensor.device)
+    ready = torch.cuda.Event()
+    ready.record()
+    _d2h_stream.wait_event(ready)
+    host = torch.empty(tuple(dev_tensor.shape), dtype=dev_tensor.dtype, pin_memory=True)
+    done = torch.cuda.Event()
+    with torch.cuda.stream(_d2h_stream):
+        host.copy_(dev_tensor, non_blocking=True)
+        done.record()
+    dev_tensor.record_stream(_d2h_stream)
+    return host, done
 
 
 _PINNED_RESULT_MAX = 1 << 30

@@ -149,6 +149,7 @@ class ScoreBatch(object):
         self._ranks_dev = None
         self._host_scores = None
         self._host_ranks = None
+        self._host_local_pending = None
 
     @property
     def n_rows(self):
@@ -175,17 +176,31 @@ class ScoreBatch(object):
             self._ranks_dev = local
         return self._ranks_dev
 
+    def prefetch_host(self):
+        """Start the device -> host copy of this rank's score rows now, on a side stream: it runs
+        beside the kernels queued after it (``Signatures.prefetch_scores``) and
+        ``host_scores_local`` / ``host_scores`` then only wait for it."""
+        if self._host_local_pending is None and self._host_scores is None and self.scores_dev.shape[0]:
+            self._host_local_pending = _engine.to_host_async(self.scores_dev[:, :self.n_cells])
+
     def host_scores_local(self):
         """This rank's rows only (no collective), in the order of ``local_rows``."""
+        if self._host_local_pending is not None:
+            host, done = self._host_local_pending
+            done.synchronize()
+            return host.numpy()
+        if self.owner_rows is None and self._host_scores is not None:
+            return self._host_scores
         return _engine.to_host(self.scores_dev[:, :self.n_cells])
 
     def host_scores(self):
         if self._host_scores is None:
-            dev = self.scores_dev
-            if self.owner_rows is not None:
+            if self.owner_rows is None:
+                self._host_scores = self.host_scores_local()
+            else:
                 from . import distributed as D
-                dev = D.all_gather_owned_rows(dev, self.owner_rows)
-            self._host_scores = _engine.to_host(dev[:, :self.n_cells])
+                dev = D.all_gather_owned_rows(self.scores_dev, self.owner_rows)
+                self._host_scores = _engine.to_host(dev[:, :self.n_cells])
         return self._host_scores
 
     def host_ranks(self):

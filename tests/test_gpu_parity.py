@@ -809,3 +809,35 @@ def test_interactive_dataframe_wrappers_vs_oracle(fp):
     np.testing.assert_allclose(cons.values, want[2], rtol=TC_CONS_RTOL)
     np.testing.assert_allclose(null.values, want[4], rtol=TC_CONS_RTOL)
     np.testing.assert_allclose(pvals.values, want[3], rtol=LOGQ_RTOL, atol=1e-6)
+
+
+def test_prefetch_scores_gives_the_same_host_arrays(fp):
+    """Signatures.prefetch_scores starts the device -> host copy of a result on a side stream;
+    the arrays read afterwards are those of the synchronous path, and the oracle's."""
+    x, w, z, genes, cells = fp.synth.make_expression(300, 257, seed=31)
+    data = fp.synth.ExpressionMatrix(x, w, genes, cells)
+    sigs = [fp.S.Signature(d, sg, "t", nm) for nm, d, sg in fp.synth.make_signature_dicts(genes, 12, seed=4)]
+    plain = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", z, 2)
+    ahead = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", z, 2)
+    fp.S.prefetch_scores(ahead)
+    fp.S.prefetch_scores(ahead)                                   # idempotent
+    want = O.calculate_sig_scores(O.ExpressionMatrix(x, w, genes, cells),
+                                  [O.Signature(s.sig_dict, s.signed, "t", s.name) for s in sigs], "weighted_avg", z, 2)
+    assert list(plain) == list(ahead) == list(want)
+    for name in want:
+        assert np.array_equal(ahead[name].scores, plain[name].scores)
+        assert np.array_equal(ahead[name].scores, want[name].scores)
+        assert np.array_equal(ahead[name].ranks, plain[name].ranks)
+    fp.S.prefetch_scores(dict())
+
+
+@pytest.mark.parametrize("n,k,kw", [(1, 2, {}), (129, 127, {}), (1001, 130, dict(outliers=1)), (4097, 260, dict(dup=3)),
+                                    (20000, 9, {}), (1000, 6, dict(binary=True))])
+def test_value_planes_staged_in_shared_memory_do_not_change_a_bit(fp, n, k, kw, monkeypatch):
+    """The value digit planes of the tensor-core path are cut from rows staged in shared memory
+    (rows that fit) or gathered from global memory: same planes, so the outputs are identical."""
+    a, staged = _tc_case(fp, n, k, 300 + n, **kw)
+    monkeypatch.setenv("FASTPROJECT_B200_ROW_STAGE", "off")
+    _, gathered = _tc_case(fp, n, k, 300 + n, **kw)
+    assert np.array_equal(staged, gathered)
+    assert np.abs(a - staged).max() <= 1e-7 * max(n, 16)
