@@ -497,7 +497,7 @@ pack_values_kernel(const double *__restrict__ values, long K, long N, long ld, l
 // time from scattered 32-byte sectors (4x the row in L2 -> SM traffic: 0.31 ms per projection at
 // 3 500 x 20 000, the L2 rate).  Here a CTA copies the row into shared memory once (bulk
 // asynchronous copies, row_tree.cuh) and permutes out of it; the next row is prefetched into L2.
-constexpr int PACK_STAGED_THREADS = 512;
+constexpr int PACK_STAGED_THREADS = 1024;
 
 template <int SR>
 __global__ void __launch_bounds__(PACK_STAGED_THREADS)
