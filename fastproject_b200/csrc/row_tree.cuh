@@ -130,7 +130,9 @@ __device__ __forceinline__ double fold_levels(double *val, const Node *__restric
         }
         __syncthreads();
     }
-    return n_int ? val[n_leaves + n_int - 1] : val[0];
+    const double root = n_int ? val[n_leaves + n_int - 1] : val[0];
+    __syncthreads();             // everybody has the root: val may be refilled (a one-leaf tree's root IS slot 0)
+    return root;
 }
 
 // one thread fills the leaf table, the program and the node table of rows of N elements

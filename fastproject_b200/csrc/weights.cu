@@ -70,26 +70,27 @@ __global__ void __launch_bounds__(W_THREADS)
 compute_weights_kernel(const double *__restrict__ X, const double *__restrict__ P_nd, const double *__restrict__ params,
                        long ldp, long G, long N, long ld, long ld_pnd, double *__restrict__ out, long ld_out,
                        const Leaf *__restrict__ leaves, int n_leaves, const Node *__restrict__ nodes, int height) {
-    extern __shared__ double val[];                      // 3 x (2 * n_leaves)
-    double *val_a = val, *val_b = val + 2 * n_leaves, *val_c = val + 4 * n_leaves;
+    extern __shared__ double val[];                      // 2 * n_leaves: one tree at a time
     for (long g = blockIdx.x; g < G; g += gridDim.x) {
         const double *row = X + g * ld;
         const double *prow = P_nd ? P_nd + g * ld_pnd : nullptr;
-        fp::rowtree::leaf_sums(DetectedValue{row, prow}, leaves, n_leaves, val_a);
-        fp::rowtree::leaf_sums(Detected{row, prow}, leaves, n_leaves, val_b);
-        fp::rowtree::leaf_sums(NotDetected{row, prow}, leaves, n_leaves, val_c);
+        fp::rowtree::leaf_sums(DetectedValue{row, prow}, leaves, n_leaves, val);
         __syncthreads();
-        const double sxp = fold_levels(val_a, nodes, n_leaves, height);
-        const double sp = fold_levels(val_b, nodes, n_leaves, height);
-        const double snd = fold_levels(val_c, nodes, n_leaves, height);
+        const double sxp = fold_levels(val, nodes, n_leaves, height);
+        fp::rowtree::leaf_sums(Detected{row, prow}, leaves, n_leaves, val);
+        __syncthreads();
+        const double sp = fold_levels(val, nodes, n_leaves, height);
+        fp::rowtree::leaf_sums(NotDetected{row, prow}, leaves, n_leaves, val);
+        __syncthreads();
+        const double snd = fold_levels(val, nodes, n_leaves, height);
         const double mu = __ddiv_rn(sxp, sp);
         double pnd = __ddiv_rn(snd, (double)N);
         double *orow = out + g * ld_out;
         // the exp and the division of the false-negative curve are evaluated once per element:
         // this sweep parks 1 - fn in the output row, the last sweep turns it into the weight
-        fp::rowtree::leaf_sums(ExpressedDetect{mu, params, ldp, orow}, leaves, n_leaves, val_a);
+        fp::rowtree::leaf_sums(ExpressedDetect{mu, params, ldp, orow}, leaves, n_leaves, val);
         __syncthreads();
-        const double mean_pde = __ddiv_rn(fold_levels(val_a, nodes, n_leaves, height), (double)N);
+        const double mean_pde = __ddiv_rn(fold_levels(val, nodes, n_leaves, height), (double)N);
         const double pe = __ddiv_rn(__dsub_rn(1.0, pnd), mean_pde);
         if (pnd == 0.0) pnd = __ddiv_rn(1.0, (double)N);           // "for stability" (:307)
         for (long c = threadIdx.x; c < N; c += blockDim.x) {
@@ -215,9 +216,9 @@ extern "C" int fp_compute_weights(const double *X, const double *p_nd, const dou
     std::vector<int> prog;
     int max_depth = 0;
     build_tree(0, N, leaves, prog, 1, max_depth);
-    const size_t smem = 6 * leaves.size() * sizeof(double);
+    const size_t smem = 2 * leaves.size() * sizeof(double);
     if (max_depth + 1 > MAX_DEPTH || smem > 200 * 1024) {
-        fp::set_error("fp_compute_weights: rows of %ld cells need %zu tree leaves (limit 4266)", (long)N,
+        fp::set_error("fp_compute_weights: rows of %ld cells need %zu tree leaves (limit 12800)", (long)N,
                       leaves.size());
         return FP_EUNSUPPORTED;
     }

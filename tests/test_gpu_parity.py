@@ -712,7 +712,7 @@ def test_compute_weights_vs_reference_golden(fp, tag):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("g,n", [(5, 1), (7, 7), (9, 8), (33, 129), (40, 1001), (64, 4097), (300, 20000), (37, 19999)])
+@pytest.mark.parametrize("g,n", [(5, 1), (7, 7), (9, 8), (33, 129), (40, 1001), (64, 4097), (300, 20000), (37, 19999), (6, 40001)])
 def test_row_kernels_staged_in_shared_memory_equal_the_global_memory_ones(fp, g, n, monkeypatch):
     """Rows that fit in shared memory are staged there once (bulk asynchronous copies) by
     fp_normalize_rows and fp_compute_weights; longer rows, rows on odd pitches and an explicit
