@@ -289,6 +289,7 @@ class ResidentJob(object):
                 e.record()
                 marks.append((stage, e))
 
+        self.last_scores = self.last_ranks = None       # the previous step's outputs go before new ones come
         mark("begin")
         scores = E.score_signatures("weighted_avg", self.wl["x"], self.wl["w"], None, self.d_ptr, self.d_gene,
                                     self.d_sign, int(self.rows.size))
@@ -522,6 +523,8 @@ def run_b200(args):
     job = ResidentJob(args.workload, cfg, wl, device, world, rank, precision)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step, launches, clocks = timed_run(job, args.steps, args.warmup, world, sampler)
+    if os.environ.get("FP_BENCH_DEBUG"):
+        sys.stderr.write("peak device memory after the timed run: %.1f GB\n" % (torch.cuda.max_memory_allocated() / 1e9))
     P = cfg["P"]
     roof, roof_s, stages = rooflines(job, ms_step, args.workload)
     result = {

@@ -532,27 +532,32 @@ class MedianOverlap(object):
     generates the weight planes of the next one (the median kernel is a bandwidth-bound sweep,
     the weight planes are FP64-bound: they share the SMs well).  Two dissimilarity buffers
     alternate; a buffer is handed back to the contraction only after the median that read it.
-    Same kernels, same arguments, same results -- only the stream differs."""
+    Same kernels, same arguments, same results -- only the stream differs.  Above
+    ``DOUBLE_BUFFER_MAX`` bytes per buffer (a million cells x thousands of signatures) there is
+    ONE buffer: the next contraction then waits for the median, which is a few per cent of it."""
+
+    DOUBLE_BUFFER_MAX = 8 << 30
 
     def __init__(self, rows, ld, device):
         global _median_stream
         if _median_stream is None:
             _median_stream = torch.cuda.Stream(device=device)
         self.side = _median_stream
-        self.bufs = [torch.empty((rows, ld), dtype=torch.float64, device=device) for _ in range(2)]
-        self.done = [None, None]
+        n_bufs = 2 if int(rows) * int(ld) * 8 <= self.DOUBLE_BUFFER_MAX else 1
+        self.bufs = [torch.empty((rows, ld), dtype=torch.float64, device=device) for _ in range(n_bufs)]
+        self.done = [None] * n_bufs
         self.turn = 0
 
     def buffer(self, rows):
         """The dissimilarity buffer for the next contraction (main stream)."""
-        k = self.turn & 1
+        k = self.turn % len(self.bufs)
         if self.done[k] is not None:
             torch.cuda.current_stream().wait_event(self.done[k])
         return self.bufs[k][:rows]
 
     def median_into(self, dis, n, dest):
         """dest[...] = row medians of ``dis`` (just written by the main stream), on the side stream."""
-        k = self.turn & 1
+        k = self.turn % len(self.bufs)
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.side):
