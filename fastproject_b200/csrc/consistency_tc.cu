@@ -50,8 +50,11 @@
 //
 // Environment: FASTPROJECT_B200_SLAB_BYTES (weight-plane budget, tests use it to run many
 // slabs at small N).  No run-time switch changes the arithmetic: the "loads only" timing
-// experiment of round 1 is a compile-time option (-DFP_TC_TIMING_NO_MMA), never part of a
-// release build.
+// experiment of round 1 is a compile-time option (-DFP_TC_TIMING_NO_MMA; its round-2 twins:
+// -DFP_TC_TIMING_NO_LOADS issues the MMAs without operand traffic, -DFP_TC_TIMING_SAME_TILE makes
+// every load an L2 hit, -DFP_TC_TIMING_TWO_STAGES shortens the pipeline, -DFP_TC_L2_PROMOTION=...
+// changes the tensor maps' L2 promotion), never part of a release build
+// (tests/cuda/mma_bound_probe.py builds them into tests/cuda/_bin/; results in DESIGN.md 6b).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,6 +65,10 @@
 #include "fp_common.cuh"
 #include "row_tree.cuh"
 #include "tc_common.cuh"
+
+#ifndef FP_TC_L2_PROMOTION
+#define FP_TC_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
 
 namespace {
 
@@ -707,7 +714,11 @@ weight_planes_kernel(const CellI *__restrict__ ci, const CellJ *__restrict__ cj,
 
 template <int SR>
 struct MmaSmem {
+#ifdef FP_TC_TIMING_TWO_STAGES
+    static constexpr int stages = 2;
+#else
     static constexpr int stages = SR == 2 ? 3 : 2;
+#endif
     static constexpr int stage_bytes = SR * A_PLANE_BYTES + WD * B_PLANE_BYTES;
     static constexpr int den_off = stages * stage_bytes;     // sum_j W_ij per column, then its scaled reciprocal
     static constexpr int rden_off = den_off + TN * 8;
@@ -782,8 +793,14 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
             // the kernel is bound by the tensor pipe.  Plain loads stay.)
             long g = 0;                                       // stages issued by this CTA so far
             for (int item = pair; item < n_items; item += n_pairs) {
+#ifdef FP_TC_TIMING_SAME_TILE
+                // timing experiment (never a release build): every pair streams the SAME operands, so
+                // every load hits L2 -- what the load path delivers without DRAM behind it
+                const long tile_row = 0, blk = rank;
+#else
                 const long tile_row = (long)(item / n_sig_pairs) * TN;       // slab-relative first cell
                 const long blk = (long)(item % n_sig_pairs) * 2 + rank;       // this CTA's block of 127 signatures
+#endif
                 // the issuer skips the products of all-zero leading weight planes (block_or): those
                 // planes are not loaded either, and a stage with nothing to add loads nothing at all
                 const uint32_t *seen_row = block_or + (long)(item / n_sig_pairs) * n_stages;
@@ -793,12 +810,30 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     const uint32_t ph = (uint32_t)(g / STAGES) & 1;
                     const uint32_t seen = seen_next;
                     if (it + 1 < n_stages) seen_next = __ldg(seen_row + it + 1);
+#ifdef FP_TC_TIMING_NO_SKIP
+                    const int tz = 0;                         // timing experiment: every plane, no block_or
+#else
                     const int tz = (it % chunk_stages == 0) ? 0 : (seen ? (__clz((int)seen) >> 3) : 4);
+#endif
+#ifdef FP_TC_SPIN_WAITS
+                    mbar_spin(&empty[s], ph ^ 1);
+#else
                     mbar_wait(&empty[s], ph ^ 1);
+#endif
                     // both producers arrive on the leader's barrier for EVERY stage (also one that loads
                     // nothing), and both CTAs' bytes are counted there: the leader cannot run ahead of a
                     // peer that has not reached the stage, so neither producer is ever lapped
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[s]), 0);
+#ifdef FP_TC_TIMING_NO_LOADS
+                    // timing experiment (never a release build): no operand traffic at all, the MMAs
+                    // run on whatever shared memory holds -- what the issue path and the tensor pipe
+                    // take by themselves
+                    if (rank == 0)
+                        mbar_arrive_expect_tx(&full[s], 0u);
+                    else
+                        mbar_arrive_cluster(leader_full);
+                    continue;
+#endif
                     if (rank == 0)
                         mbar_arrive_expect_tx(&full[s], tz == 4 ? 0u
                                                                 : 2u * (uint32_t)(SR * A_PLANE_BYTES +
@@ -839,12 +874,20 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                     const uint32_t seen = seen_next;
                     if (it + 1 < n_stages) seen_next = __ldg(seen_row + it + 1);
                     // leading all-zero planes: their products are exactly zero (4: nothing to add at all)
+#ifdef FP_TC_TIMING_NO_SKIP
+                    const int tz = 0;
+#else
                     const int tz = seen ? (__clz((int)seen) >> 3) : 4;
+#endif
                     if (chunk_first && c > 0) {
                         mbar_wait_cluster(tmem_empty, (uint32_t)(c - 1) & 1);   // epilogues of both CTAs drained TMEM
                         tc_fence_after_sync();
                     }
+#ifdef FP_TC_SPIN_WAITS
+                    mbar_spin_cluster(&full[s], ph);
+#else
                     mbar_wait_cluster(&full[s], ph);          // both CTAs' operands of this stage
+#endif
                     tc_fence_after_sync();
                     if (elect_one()) {
                         const uint64_t a_st = a_desc_base + (uint64_t)(s * (L::stage_bytes >> 4));
@@ -867,7 +910,14 @@ consistency_mma_kernel(const __grid_constant__ CUtensorMap tmap_values, const __
                             }
                         }
 #endif
+#ifdef FP_TC_TIMING_PLAIN_ARRIVE
+                        // timing experiment with -DFP_TC_TIMING_NO_MMA only (there is nothing to commit):
+                        // the stage is handed back by plain arrivals instead of tcgen05.commit
+                        mbar_arrive(&empty[s]);
+                        mbar_arrive_cluster(mapa_shared(smem_u32(&empty[s]), 1));
+#else
                         umma_commit_pair(&empty[s]);          // frees the stage in both CTAs
+#endif
                         if (chunk_last) umma_commit_pair(accum_full);
                     }
                     __syncwarp();
@@ -1322,7 +1372,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         FP_TC_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             fp::set_error("fp_consistency: cuTensorMapEncodeTiled failed (%d)", (int)r);
             return FP_ECUDA;
@@ -1346,7 +1396,7 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wplanes, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         FP_TC_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             fp::set_error("fp_consistency: cuTensorMapEncodeTiled (weights) failed (%d)", (int)r);
             return FP_ECUDA;
