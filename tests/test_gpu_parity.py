@@ -841,3 +841,18 @@ def test_value_planes_staged_in_shared_memory_do_not_change_a_bit(fp, n, k, kw, 
     _, gathered = _tc_case(fp, n, k, 300 + n, **kw)
     assert np.array_equal(staged, gathered)
     assert np.abs(a - staged).max() <= 1e-7 * max(n, 16)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_single_dissimilarity_buffer_gives_the_same_result(fp, precision, monkeypatch):
+    """Above MedianOverlap.DOUBLE_BUFFER_MAX bytes (a million cells) the medians and the next
+    contraction share ONE dissimilarity buffer and take turns; forcing that at test size must
+    not change a bit of the result."""
+    c = G.load("case_synth_odd")
+    two = _svp(fp, c, precision=precision)
+    monkeypatch.setattr(fp.E.MedianOverlap, "DOUBLE_BUFFER_MAX", 0)
+    one = _svp(fp, c, precision=precision)
+    assert two[0] == one[0] and two[1] == one[1] and two[5] == one[5]
+    for a, b in zip(two[2:5], one[2:5]):
+        assert np.array_equal(a, b)
+    _check_svp(one, c, "svp", rtol=_rtol(precision))
