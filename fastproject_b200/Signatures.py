@@ -23,6 +23,31 @@ from .SigScoreMethods import SignatureScores
 
 # cache of the permutation background of the precomputed-numeric branch (:16-27)
 _bg_dist = np.zeros((0, 0))
+# its device twin: (the host array it was made from, [R x n] int64 CUDA tensor).  The host array
+# is this module's own state (get_bg_dist replaces it, never edits it), so its identity says
+# whether the device copy is current; kept only while it is small (1 GiB).
+_bg_dist_dev = None
+_BG_DEVICE_CACHE_MAX = 1 << 30
+
+
+def _drop_bg_device():
+    global _bg_dist_dev
+    _bg_dist_dev = None
+
+
+_engine._clear_hooks.append(_drop_bg_device)
+
+
+def _bg_permutations_device(perm):
+    """[R x n] row permutations of ``get_bg_dist`` on the device.  A precomputed signature is
+    tested against every projection with the SAME 10 000 permutations: uploading (and
+    transposing) 160 MB per call was most of the time of this branch at 2 000 cells."""
+    global _bg_dist_dev
+    if _bg_dist_dev is not None and _bg_dist_dev[0] is perm:
+        return _bg_dist_dev[1]
+    dev_perm = _engine.to_device(perm, torch.long).t().contiguous()          # transposed on the device
+    _bg_dist_dev = (perm, dev_perm) if perm.nbytes <= _BG_DEVICE_CACHE_MAX else None
+    return dev_perm
 
 
 def get_bg_dist(N_SAMPLES, NUM_REPLICATES):
@@ -443,8 +468,7 @@ def _precomputed_numeric(sig_scores, coords, sig2, n, precision, compute=True):
     r_dev = _engine.to_device(r)
     rows = torch.zeros((NUM_REPLICATES + 1, ld), dtype=torch.float64, device=dev)
     rows[0, :n] = r_dev
-    perm_dev = _engine.to_device(np.ascontiguousarray(perm.T), torch.long)   # (R, n)
-    rows[1:, :n] = r_dev[perm_dev]
+    rows[1:, :n] = r_dev[_bg_permutations_device(perm)]                      # (R, n)
     dis = _engine.consistency(coords, sig2, rows, n, precision=precision, any_cell_order=True)
     med = _engine.row_medians(dis, n)
     p, sd = _single_group_pvalue(med[0], med[1:])

@@ -371,9 +371,14 @@ class resident(object):
         return False
 
 
+_clear_hooks = []       # other modules' device-side state (Signatures' permutation background)
+
+
 def clear_device_cache():
     expression_cache.clear()
     _ws_cache.clear()
+    for hook in _clear_hooks:
+        hook()
 
 
 # --------------------------------------------------------------------------
