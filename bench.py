@@ -300,10 +300,17 @@ class ResidentJob(object):
             ranks = D.all_gather_rank_rows(ranks, self.owner_rows, N)
             self.med_all.zero_()
         mark("gather")
+        # (what Signatures._contract_runs does) row ranges met by several projections are packed once
+        uses, packed = dict(), dict()
+        for _, lo, hi in self.runs:
+            uses[(lo, hi)] = uses.get((lo, hi), 0) + 1
         for p, lo, hi in self.runs:
+            if uses[(lo, hi)] > 1 and (lo, hi) not in packed:
+                packed[(lo, hi)] = E.pack_values(ranks[lo:hi], N, precision=self.precision)
             # the median of this run goes to a side stream and overlaps the next run's weight planes
             dis = E.consistency(self.coords[p], self.sig2, ranks[lo:hi], N, out=self.overlap.buffer(hi - lo),
-                                precision=self.precision, slot="bench", any_cell_order=True)
+                                precision=self.precision, slot="bench", any_cell_order=True,
+                                packed=packed.get((lo, hi)))
             mark("consistency")
             self.overlap.median_into(dis, N, self.med_all[p, lo:hi])
         self.overlap.join()

@@ -424,13 +424,22 @@ def _contract_runs(runs, coords_all, sig2, ranks, n, overlap, med_all, precision
                                           precision="fp64", slot="svp", any_cell_order=True)
                 overlap.median_into(dis, n, med_all[p, lo:hi])
 
+    # row ranges contracted against more than one projection (a single GPU: all of them) are
+    # packed once -- value range and digit planes -- and only permuted per projection
+    uses = dict()
+    for _, lo, hi in runs:
+        uses[(lo, hi)] = uses.get((lo, hi), 0) + 1
+    packed = dict()
     for r, (p, lo, hi) in enumerate(runs):
         view = ranks[lo:hi]
         if pending is not None and pending[0].shape[0] != view.shape[0]:
             settle(pending)             # the flag lives in a workspace laid out for that shape
             pending = None
+        if uses[(lo, hi)] > 1 and (lo, hi) not in packed:
+            packed[(lo, hi)] = _engine.pack_values(view, n, precision=requested)
         dis = _engine.consistency(coords_all[p], sig2, view, n, out=overlap.buffer(hi - lo),
-                                  precision=requested, slot="svp", any_cell_order=True)   # only the median is taken
+                                  precision=requested, slot="svp", any_cell_order=True,
+                                  packed=packed.get((lo, hi)))                            # only the median is taken
         overlap.median_into(dis, n, med_all[p, lo:hi])
         pending = (view, (pending[1] if pending else []) + [r])
     if while_running is not None:

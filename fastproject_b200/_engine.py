@@ -462,11 +462,39 @@ def normalize_cols(x):
     return out
 
 
+class PackedValues(object):
+    """The values of ``consistency`` in the form the tensor-core mode contracts them
+    (``fp_values_pack``: value range, digit planes in the caller's cell order, refusal flag).
+    ``sigs_vs_projections`` tests one rank matrix against every projection: packed once, a
+    projection only permutes the planes into its own cell order."""
+
+    PACK_MAX_BYTES = 2 << 30
+
+    def __init__(self, buf, k, n):
+        self.buf, self.k, self.n = buf, int(k), int(n)
+
+
+def pack_values(ranks, n, precision=None):
+    """``PackedValues`` of the [K x ld] CUDA float64 matrix, or None when the mode in force is not
+    the tensor-core one (or the planes would be too large to keep beside the matrix)."""
+    k = ranks.shape[0]
+    if not k or resolve_precision(precision, n) != "tc":
+        return None
+    nbytes = _native.query("fp_values_pack_bytes", n, k)
+    if not nbytes or nbytes > PackedValues.PACK_MAX_BYTES:
+        return None
+    buf = torch.empty((nbytes,), dtype=torch.uint8, device=ranks.device)
+    _native.call("fp_values_pack", ptr(ranks), k, n, ranks.stride(0), ptr(buf), nbytes, stream_ptr())
+    return PackedValues(buf, k, n)
+
+
 def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_ABS_ERROR,
-                precision=None, slot="default", any_cell_order=False):
+                precision=None, slot="default", any_cell_order=False, packed=None):
     """coords: [2 x N] CUDA float64; ranks [K x ld]; sigma_sq float or [N] tensor.
     ``any_cell_order``: the caller only reduces the rows over the cells (median): the columns may
     come in the library's own cell order (saves scattered writes on the tensor-core path).
+    ``packed``: ``pack_values(ranks, n)`` of the same matrix -- the call then reads the packed
+    form instead of ``ranks`` (same result, bit for bit).
     Asynchronous.  The tensor-core mode refuses values it cannot represent exactly (the output
     is then NaN): ``consistency_refused`` tells, after the calls on a workspace ``slot``."""
     k, ld = ranks.shape
@@ -479,6 +507,12 @@ def consistency(coords, sigma_sq, ranks, n, out=None, output_kind=_native.OUT_AB
     ws, ws_ptr = _workspace(nbytes, ranks.device, slot)
     if any_cell_order:
         output_kind |= _native.OUT_ANY_CELL_ORDER
+    if packed is not None and mode == _native.PRECISION_CODES["tc"]:
+        if (packed.k, packed.n) != (k, int(n)):
+            raise ValueError("packed values of a %d x %d matrix given for %d x %d" % (packed.k, packed.n, k, n))
+        _native.call("fp_consistency_packed", ptr(coords), ptr(vec), scalar, ptr(packed.buf), n, k,
+                     ptr(out), out.stride(0), output_kind, ws_ptr, nbytes, stream_ptr())
+        return out
     _native.call("fp_consistency", ptr(coords), ptr(vec), scalar, ptr(ranks), n, k, ld,
                  ptr(out), out.stride(0), output_kind, mode, ws_ptr, nbytes, stream_ptr())
     return out

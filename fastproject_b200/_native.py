@@ -39,6 +39,10 @@ SIGNATURES = {
     "fp_consistency": (c_int, [c_ptr, c_ptr, c_f64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64,
                                c_int, c_int, c_ptr, c_size, c_ptr]),
     "fp_consistency_status": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr]),
+    "fp_values_pack_bytes": (c_size, [c_i64, c_i64]),
+    "fp_values_pack": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_size, c_ptr]),
+    "fp_consistency_packed": (c_int, [c_ptr, c_ptr, c_f64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int, c_ptr, c_size,
+                                      c_ptr]),
     "fp_compute_weights_workspace_bytes": (c_size, [c_i64]),
     "fp_compute_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr,
                                    c_size, c_ptr]),

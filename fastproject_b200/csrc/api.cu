@@ -13,9 +13,12 @@ int fp_consistency_fp64(const double *coords, const double *sigma_sq, double sig
 
 size_t fp_consistency_tc_workspace_bytes(int64_t N, int64_t K);
 int fp_consistency_tc_status(const void *workspace, int64_t N, int64_t K, cudaStream_t st);
+size_t fp_values_pack_tc_bytes(int64_t N, int64_t K);
+int fp_values_pack_tc(const double *values, int64_t K, int64_t N, int64_t ld, void *packed, size_t packed_bytes,
+                      cudaStream_t st);
 int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
-                      const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
-                      int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st);
+                      const double *values, const void *packed, int64_t N, int64_t K, int64_t ld, double *out,
+                      int64_t ld_out, int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
 namespace fp {
 
@@ -74,10 +77,35 @@ extern "C" int fp_consistency(const double *coords, const double *sigma_sq, doub
         return fp_consistency_fp64(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim,
                                    ld_out, output_kind & ~FP_OUT_ANY_CELL_ORDER, fp::as_stream(stream));
     if (precision_mode == FP_PRECISION_TC)
-        return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, ranks, N, K, ld, out_dissim, ld_out,
+        return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, ranks, nullptr, N, K, ld, out_dissim, ld_out,
                                  output_kind, workspace, workspace_bytes, fp::as_stream(stream));
     fp::set_error("fp_consistency: unknown precision mode %d", precision_mode);
     return FP_EUNSUPPORTED;
+}
+
+extern "C" size_t fp_values_pack_bytes(int64_t N, int64_t K) { return fp_values_pack_tc_bytes(N, K); }
+
+extern "C" int fp_values_pack(const double *values, int64_t K, int64_t N, int64_t ld, void *packed, size_t packed_bytes,
+                              void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(values && packed, "fp_values_pack: null pointer");
+    FP_CHECK_ARG(N > 0 && K > 0 && ld >= N, "fp_values_pack: bad shape N=%ld K=%ld ld=%ld", (long)N, (long)K, (long)ld);
+    return fp_values_pack_tc(values, K, N, ld, packed, packed_bytes, fp::as_stream(stream));
+}
+
+extern "C" int fp_consistency_packed(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                                     const void *packed, int64_t N, int64_t K, double *out_dissim, int64_t ld_out,
+                                     int output_kind, void *workspace, size_t workspace_bytes, void *stream) {
+    fp::clear_error();
+    FP_CHECK_ARG(coords && packed && out_dissim, "fp_consistency_packed: null pointer");
+    FP_CHECK_ARG(N > 0 && K > 0 && ld_out >= N, "fp_consistency_packed: bad shape N=%ld K=%ld ld_out=%ld", (long)N,
+                 (long)K, (long)ld_out);
+    FP_CHECK_ARG(sigma_sq || sigma_sq_scalar > 0.0, "fp_consistency_packed: sigma_sq must be positive");
+    FP_CHECK_ARG((output_kind & ~FP_OUT_ANY_CELL_ORDER) == FP_OUT_ABS_ERROR ||
+                     (output_kind & ~FP_OUT_ANY_CELL_ORDER) == FP_OUT_PREDICTION,
+                 "fp_consistency_packed: unknown output kind %d", output_kind);
+    return fp_consistency_tc(coords, sigma_sq, sigma_sq_scalar, nullptr, packed, N, K, 0, out_dissim, ld_out,
+                             output_kind, workspace, workspace_bytes, fp::as_stream(stream));
 }
 
 namespace {

@@ -583,6 +583,34 @@ pack_values_staged_kernel(const double *__restrict__ values, long K, long N, lon
     if (bad) atomicOr(flag, 1);
 }
 
+// Packed values (fp_values_pack) hold the digit planes in the CALLER's cell order; a projection
+// needs them in its own order.  One CTA per plane row: the row (Npad bytes) is copied to shared
+// memory, then written out permuted, four cells per store.  Rows too long for shared memory are
+// gathered from global memory.
+constexpr int PERMUTE_THREADS = 256;
+constexpr long PERMUTE_SMEM_MAX = 200 * 1024;
+
+__global__ void __launch_bounds__(PERMUTE_THREADS)
+permute_planes_kernel(const int8_t *__restrict__ src, int8_t *__restrict__ dst, const int32_t *__restrict__ order,
+                      long N, long Npad, int staged) {
+    extern __shared__ __align__(16) int8_t prow[];
+    const int8_t *row = src + (long)blockIdx.x * Npad;
+    int8_t *out = dst + (long)blockIdx.x * Npad;
+    if (staged) {
+        for (long i = (long)threadIdx.x * 16; i < Npad; i += PERMUTE_THREADS * 16)
+            *reinterpret_cast<uint4 *>(prow + i) = *reinterpret_cast<const uint4 *>(row + i);
+        __syncthreads();
+    }
+    const int8_t *from = staged ? prow : row;
+    for (long j4 = (long)threadIdx.x * 4; j4 < Npad; j4 += PERMUTE_THREADS * 4) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (j4 + e < N) word |= (uint32_t)(uint8_t)from[order[j4 + e]] << (8 * e);
+        *reinterpret_cast<uint32_t *>(out + j4) = word;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // 2^t * (2^32 - 1), t <= 0, rounded to nearest: the fixed-point weight.
 // t = n + k/128 + g (|g| <= 2^-8): table for 2^(k/128), cubic for 2^g - 1
@@ -1237,9 +1265,77 @@ int fp_consistency_tc_status(const void *workspace, int64_t N, int64_t K, cudaSt
     return FP_OK;
 }
 
+// digit planes of `values` (through `order` when given), staged kernel for rows that fit in
+// shared memory
+int launch_pack_values(const Plan &p, const double *values, int64_t K, int64_t N, int64_t ld, const int32_t *order,
+                       int8_t *planes, const unsigned long long *range, int *flag, cudaStream_t st) {
+    const size_t staged_b = (size_t)((N + 1) & ~1L) * sizeof(double);
+    if (fp::rowtree::stage_applies(values, ld, staged_b)) {
+        static size_t staged_set[2] = {0, 0};
+        auto kernel = p.sr == 2 ? pack_values_staged_kernel<2> : pack_values_staged_kernel<3>;
+        if (staged_b > staged_set[p.sr == 3]) {
+            FP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_b));
+            staged_set[p.sr == 3] = staged_b;
+        }
+        long blocks = (long)fp::sm_count() * (staged_b <= 100 * 1024 ? 2 : 1);
+        if (blocks > p.Kpad) blocks = p.Kpad;
+        kernel<<<(unsigned)blocks, PACK_STAGED_THREADS, staged_b, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes,
+                                                                       range, flag);
+        FP_CHECK_LAUNCH("pack_values_staged_kernel");
+    } else {
+        dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
+        if (p.sr == 2)
+            pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
+        else
+            pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
+        FP_CHECK_LAUNCH("pack_values_kernel");
+    }
+    return FP_OK;
+}
+
+// header of a packed-values blob (fp_values_pack): value range keys [3], then the refusal flag
+constexpr size_t PACKED_FLAG_OFF = 32, PACKED_PLANES_OFF = 256;
+
+size_t fp_values_pack_tc_bytes(int64_t N, int64_t K) {
+    Plan p;
+    if (N <= 0 || K <= 0 || !make_plan(N, K, &p)) return 0;
+    return PACKED_PLANES_OFF + (size_t)p.sr * p.Kpad * p.Npad;
+}
+
+// value range + digit planes of `values` in the caller's cell order, into `packed`
+int fp_values_pack_tc(const double *values, int64_t K, int64_t N, int64_t ld, void *packed, size_t packed_bytes,
+                      cudaStream_t st) {
+    Plan p;
+    if (!make_plan(N, K, &p)) {
+        fp::set_error("fp_values_pack: FP_PRECISION_TC supports N <= 4000000 cells (N=%ld)", (long)N);
+        return FP_EUNSUPPORTED;
+    }
+    const size_t need = PACKED_PLANES_OFF + (size_t)p.sr * p.Kpad * p.Npad;
+    if (!packed || packed_bytes < need) {
+        fp::set_error("fp_values_pack: buffer %zu bytes < required %zu", packed_bytes, need);
+        return FP_EWORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(packed) & 255) != 0) {
+        fp::set_error("fp_values_pack: buffer must be 256-byte aligned");
+        return FP_EINVAL;
+    }
+    char *pk = static_cast<char *>(packed);
+    unsigned long long *range = reinterpret_cast<unsigned long long *>(pk);
+    int *flag = reinterpret_cast<int *>(pk + PACKED_FLAG_OFF);
+    int8_t *planes = reinterpret_cast<int8_t *>(pk + PACKED_PLANES_OFF);
+    FP_CHECK_CUDA(cudaMemsetAsync(pk, 0, PACKED_PLANES_OFF, st));
+    FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
+    unsigned gy = (unsigned)(K < 296 ? K : 296);
+    unsigned gx = (unsigned)((N + 2047) / 2048);
+    if (gx > 4) gx = 4;
+    value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
+    FP_CHECK_LAUNCH("value_range_kernel");
+    return launch_pack_values(p, values, K, N, ld, nullptr, planes, range, flag, st);
+}
+
 int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
-                      const double *values, int64_t N, int64_t K, int64_t ld, double *out, int64_t ld_out,
-                      int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                      const double *values, const void *packed, int64_t N, int64_t K, int64_t ld, double *out,
+                      int64_t ld_out, int output_kind, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Plan p;
     if (!make_plan(N, K, &p)) {
         fp::set_error("fp_consistency: FP_PRECISION_TC supports N <= 4000000 cells (N=%ld)", (long)N);
@@ -1335,33 +1431,39 @@ int fp_consistency_tc(const double *coords, const double *sigma_sq, double sigma
         // skipped this; a wrong assertion gave silently wrong results, and verifying it costs as much
         // as packing.)
         FP_CHECK_CUDA(cudaMemsetAsync(flag, 0, 64, st));
-        FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
-        FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
-        unsigned gy = (unsigned)(K < 296 ? K : 296);
-        unsigned gx = (unsigned)((N + 2047) / 2048);
-        if (gx > 4) gx = 4;
-        value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
-        FP_CHECK_LAUNCH("value_range_kernel");
-        const size_t staged_b = (size_t)((N + 1) & ~1L) * sizeof(double);
-        if (fp::rowtree::stage_applies(values, ld, staged_b)) {
-            static size_t staged_set[2] = {0, 0};
-            auto kernel = p.sr == 2 ? pack_values_staged_kernel<2> : pack_values_staged_kernel<3>;
-            if (staged_b > staged_set[p.sr == 3]) {
-                FP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_b));
-                staged_set[p.sr == 3] = staged_b;
+        if (packed) {
+            // the values arrive as fp_values_pack left them: range and refusal flag in the header, digit
+            // planes in the caller's cell order -- only the permutation to this projection's order is left
+            const char *pk = static_cast<const char *>(packed);
+            FP_CHECK_CUDA(cudaMemcpyAsync(range, pk, 24, cudaMemcpyDeviceToDevice, st));
+            FP_CHECK_CUDA(cudaMemcpyAsync(flag, pk + PACKED_FLAG_OFF, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            const int8_t *planes0 = reinterpret_cast<const int8_t *>(pk + PACKED_PLANES_OFF);
+            const size_t plane_bytes = (size_t)p.sr * p.Kpad * p.Npad;
+            if (!order) {
+                FP_CHECK_CUDA(cudaMemcpyAsync(planes, planes0, plane_bytes, cudaMemcpyDeviceToDevice, st));
+            } else {
+                const int staged = p.Npad <= PERMUTE_SMEM_MAX;
+                const size_t smem = staged ? (size_t)p.Npad : 0;
+                static size_t smem_set = 0;
+                if (smem > 40 * 1024 && smem > smem_set) {
+                    FP_CHECK_CUDA(cudaFuncSetAttribute(permute_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)smem));
+                    smem_set = smem;
+                }
+                permute_planes_kernel<<<(unsigned)(p.sr * p.Kpad), PERMUTE_THREADS, smem, st>>>(planes0, planes, order, N,
+                                                                                             p.Npad, staged);
+                FP_CHECK_LAUNCH("permute_planes_kernel");
             }
-            long blocks = (long)fp::sm_count() * (staged_b <= 100 * 1024 ? 2 : 1);
-            if (blocks > p.Kpad) blocks = p.Kpad;
-            kernel<<<(unsigned)blocks, PACK_STAGED_THREADS, staged_b, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes,
-                                                                           range, flag);
-            FP_CHECK_LAUNCH("pack_values_staged_kernel");
         } else {
-            dim3 grid((unsigned)((p.Npad / 4 + 255) / 256), (unsigned)p.Kpad);
-            if (p.sr == 2)
-                pack_values_kernel<2><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
-            else
-                pack_values_kernel<3><<<grid, 256, 0, st>>>(values, K, N, ld, p.Kpad, p.Npad, order, planes, range, flag);
-            FP_CHECK_LAUNCH("pack_values_kernel");
+            FP_CHECK_CUDA(cudaMemsetAsync(range, 0xff, 8, st));
+            FP_CHECK_CUDA(cudaMemsetAsync(range + 1, 0, 16, st));
+            unsigned gy = (unsigned)(K < 296 ? K : 296);
+            unsigned gx = (unsigned)((N + 2047) / 2048);
+            if (gx > 4) gx = 4;
+            value_range_kernel<<<dim3(gx, gy), 256, 0, st>>>(values, K, N, ld, range);
+            FP_CHECK_LAUNCH("value_range_kernel");
+            const int rc = launch_pack_values(p, values, K, N, ld, order, planes, range, flag, st);
+            if (rc != FP_OK) return rc;
         }
     }
     CUtensorMap tmap, tmap_w;

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define FP_ABI_VERSION 2
+#define FP_ABI_VERSION 3
 
 /* error codes */
 #define FP_OK            0
@@ -243,6 +243,25 @@ int fp_consistency(const double *coords, const double *sigma_sq, double sigma_sq
                    const double *ranks, int64_t N, int64_t K, int64_t ld,
                    double *out_dissim, int64_t ld_out, int output_kind, int precision_mode,
                    void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Packed values -- the values of fp_consistency in the form FP_PRECISION_TC contracts them.
+ * sigs_vs_projections tests the SAME rank matrix against every projection
+ * (Signatures.py:359-369 builds it once, the loop :388-446 reuses it): fp_values_pack reads the
+ * matrix once (value range, balanced base-256 digit planes in the caller's cell order, refusal
+ * flag) into a caller-owned buffer, and fp_consistency_packed takes that buffer INSTEAD of the
+ * matrix, so a projection only permutes the digit planes into its own cell order.  The buffer
+ * is the input: there is no second copy of the values it could disagree with.  Same results,
+ * bit for bit, as fp_consistency(FP_PRECISION_TC) on the matrix; fp_consistency_status reports
+ * refused values in the same way.
+ *   packed : fp_values_pack_bytes(N, K) bytes (0: shape not supported), 256-byte aligned
+ */
+size_t fp_values_pack_bytes(int64_t N, int64_t K);
+int fp_values_pack(const double *values, int64_t K, int64_t N, int64_t ld, void *packed, size_t packed_bytes,
+                   void *stream);
+int fp_consistency_packed(const double *coords, const double *sigma_sq, double sigma_sq_scalar,
+                          const void *packed, int64_t N, int64_t K, double *out_dissim, int64_t ld_out,
+                          int output_kind, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * fp_row_medians -- exact median over the N entries of each of K rows

@@ -39,7 +39,7 @@ def test_ctypes_table_matches_header(lib):
 
 
 def test_version_and_error_text(lib):
-    assert lib.fp_abi_version() == 2
+    assert lib.fp_abi_version() == 3
     assert b"sm_100a" in lib.fp_version()
     assert isinstance(lib.fp_last_error(), bytes)
 

@@ -856,3 +856,64 @@ def test_single_dissimilarity_buffer_gives_the_same_result(fp, precision, monkey
     for a, b in zip(two[2:5], one[2:5]):
         assert np.array_equal(a, b)
     _check_svp(one, c, "svp", rtol=_rtol(precision))
+
+
+@pytest.mark.parametrize("n,k,kw", [(1, 2, {}), (129, 127, {}), (1000, 5, dict(outliers=2)), (4097, 260, dict(dup=3)),
+                                    (6000, 40, dict(per_cell=True)), (20000, 9, {}), (33000, 3, dict(outliers=1)),
+                                    (5000, 6, dict(binary=True))])
+def test_packed_values_give_the_same_bits_as_the_matrix(fp, n, k, kw):
+    """fp_values_pack + fp_consistency_packed (the value range and the digit planes made once,
+    permuted per projection) against fp_consistency on the matrix itself: identical outputs, in
+    the caller's cell order, in any cell order (as multisets per row) and for the raw prediction;
+    two projections from one packed buffer."""
+    import torch
+    from scipy.stats import rankdata
+    rng = np.random.RandomState(500 + n)
+    proj, _ = fp.synth.make_projections(n, 2, seed=n)
+    ld = fp.E.padded(n)
+    if kw.get("binary"):
+        vals = (rng.uniform(size=(k, n)) < 0.3).astype(np.float64)
+    else:
+        vals = np.array([rankdata(np.round(rng.normal(size=n), 2 if r % 2 else 6)) for r in range(k)])
+    dev = torch.zeros((k, ld), dtype=torch.float64, device="cuda")
+    dev[:, :n] = torch.from_numpy(vals).cuda()
+    packed = fp.E.pack_values(dev, n, precision="tc")
+    assert packed is not None and (packed.k, packed.n) == (k, n)
+    for name in sorted(proj):
+        c = torch.from_numpy(proj[name].copy()).cuda()
+        if kw.get("outliers"):
+            c[:, 0] = torch.tensor([7.0, -6.0], dtype=torch.float64)
+        if kw.get("dup"):
+            c[:, n - 1] = c[:, 5]
+        sig = 0.33 ** 2
+        if kw.get("per_cell"):
+            sig = torch.from_numpy((0.2 + 0.3 * rng.uniform(size=n)) ** 2).cuda()
+        for kind in (0, 1):                                   # |rank - prediction|, prediction
+            a = fp.E.consistency(c, sig, dev, n, precision="tc", output_kind=kind)[:, :n].cpu().numpy()
+            b = fp.E.consistency(c, sig, dev, n, precision="tc", output_kind=kind, packed=packed)[:, :n].cpu().numpy()
+            assert np.array_equal(a, b)
+        a = fp.E.consistency(c, sig, dev, n, precision="tc", any_cell_order=True)[:, :n].cpu().numpy()
+        b = fp.E.consistency(c, sig, dev, n, precision="tc", any_cell_order=True, packed=packed)[:, :n].cpu().numpy()
+        assert np.array_equal(a, b)
+        assert not fp.E.consistency_refused(dev, n, precision="tc")
+    with pytest.raises(ValueError):
+        fp.E.consistency(c, 0.1, dev[:1], n, precision="tc", packed=packed)
+    # FP64 mode ignores the packed form (and nothing is packed for it)
+    assert fp.E.pack_values(dev, n, precision="fp64") is None
+
+
+def test_packed_values_carry_the_refusal(fp):
+    """Values the tensor-core mode cannot hold exactly are refused at packing time; every call on
+    the packed buffer then returns NaN and reports it, like the call on the matrix."""
+    import torch
+    n, k = 5000, 4
+    rng = np.random.RandomState(3)
+    proj, _ = fp.synth.make_projections(n, 1, seed=2)
+    c = torch.from_numpy(proj["Proj00"]).cuda()
+    vals = rng.normal(size=(k, n))                            # not half-integers
+    dev = torch.zeros((k, fp.E.padded(n)), dtype=torch.float64, device="cuda")
+    dev[:, :n] = torch.from_numpy(vals).cuda()
+    packed = fp.E.pack_values(dev, n, precision="tc")
+    out = fp.E.consistency(c, 0.33 ** 2, dev, n, precision="tc", packed=packed, slot="refusal")[:, :n]
+    assert fp.E.consistency_refused(dev, n, precision="tc", slot="refusal")
+    assert bool(torch.isnan(out).all())
