@@ -917,3 +917,39 @@ def test_packed_values_carry_the_refusal(fp):
     out = fp.E.consistency(c, 0.33 ** 2, dev, n, precision="tc", packed=packed, slot="refusal")[:, :n]
     assert fp.E.consistency_refused(dev, n, precision="tc", slot="refusal")
     assert bool(torch.isnan(out).all())
+
+
+def test_integration_md_ctypes_stub_runs(fp):
+    """The ctypes binding printed in INTEGRATION.md section 2 is executed as it stands (only the
+    library path is made absolute): its scores equal the mirror's, its medians -- one projection
+    at a time and through the packed-values loop -- equal each other and the engine's."""
+    import os
+    import re
+    import torch
+    from scipy.stats import rankdata
+    from fastproject_b200 import _native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# FastProject/_b200\.py.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("libfastproject_b200.so")', "ctypes.CDLL(%r)" % _native.LIB_PATH)
+    ns = dict()
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    n, k = 5000, 40
+    rng = np.random.RandomState(8)
+    proj, _ = fp.synth.make_projections(n, 2, seed=3)
+    coords = [torch.from_numpy(proj[name].copy()).cuda() for name in sorted(proj)]
+    ranks = torch.from_numpy(np.array([rankdata(rng.normal(size=n)) for _ in range(k)])).cuda()
+    meds = ns["median_dissimilarities"](coords, ranks)
+    for i, c in enumerate(coords):
+        one = ns["median_dissimilarity"](c, ranks)
+        assert torch.equal(meds[i], one)
+        dis = fp.E.consistency(c, 0.33 ** 2, ranks, n, precision="tc")
+        assert torch.equal(one, fp.E.row_medians(dis, n))
+    x, w, z, genes, cells = fp.synth.make_expression(300, 256, seed=5)
+    data = fp.synth.ExpressionMatrix(x, w, genes, cells)
+    sigs = [fp.S.Signature(d, sg, "t", nm) for nm, d, sg in fp.synth.make_signature_dicts(genes, 6, seed=2)]
+    from fastproject_b200 import _scoring
+    kept, ptr_, gene, sign, _ = _scoring.pack_signatures(sigs, genes, 1)
+    got = ns["weighted_scores"](data, ptr_, gene, sign).cpu().numpy()
+    want = fp.S.calculate_sig_scores(data, sigs, "weighted_avg", z, 1)
+    assert np.array_equal(got, np.array([want[sigs[p].name].scores for p in kept]))
